@@ -1,0 +1,667 @@
+// C-ABI of the B200-native beetroots sampler step: context, uploads and kernel orchestration.
+// Entry points are declared (with the reference interface each replaces) in include/beetroots_b200.h.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "mlp_simt.cuh"
+#include "sampler_kernels.cuh"
+#include "mlp_tc.cuh"
+
+static thread_local std::string g_err;
+static int fail(const char* what, const char* file, int line, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s:%d: %s: %s", file, line, what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s:%d: %s", file, line, what);
+    g_err = buf;
+    return e != cudaSuccess ? -(int)e - 1000 : -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, __FILE__, __LINE__, e_); } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) return fail(msg, __FILE__, __LINE__); } while (0)
+#define KLAUNCH(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail("kernel launch", __FILE__, __LINE__, e_); } while (0)
+
+struct bt_ctx {
+    int device = 0, N = 0, D = 0, L = 0, max_degree = 0;
+    cudaStream_t stream = 0;
+    int mlp_mode = BT_MLP_FP32;
+    int64_t launches = 0;
+    int sm_count = 148;
+    // network
+    NetDev net{};
+    FmapDev fm{};
+    bool have_net = false, have_fm = false, have_obs = false, have_graph = false, have_priors = false;
+    std::vector<void*> net_allocs;
+    std::vector<double> shift;          // per-line output bias (natural log), added back on the host side
+    TcNet tc{};                         // bf16 tensor-core copy of the weights (mlp_tc.cuh)
+    // data
+    ObsConst* obs = nullptr;
+    PriorDev pr{};
+    int* nbr = nullptr;
+    int64_t* gid = nullptr;
+    int n_sites = 0;
+    std::vector<int> site_size, site_off;
+    int* site_pix = nullptr;            // concatenated
+    // state
+    float *theta = nullptr, *v = nullptr, *nll_lik = nullptr, *grad_lik = nullptr, *lf_cache = nullptr;
+    int* jt = nullptr;
+    float *accept = nullptr, *logpa = nullptr;
+    uint8_t* accepted_any = nullptr;
+    // scratch (grown on demand)
+    float *rows = nullptr, *lf_rows = nullptr, *jac_rows = nullptr, *nl = nullptr, *logq = nullptr, *objc = nullptr;
+    size_t rows_cap = 0, jac_cap = 0;
+    float* tmpf = nullptr;              // N * max(D, L) float staging
+    double* tmpd = nullptr;             // reductions
+    uint8_t* owned_dev = nullptr;
+    // host staging
+    std::vector<float> hf;
+    // profiling of the forward-map kernel
+    bool prof = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double prof_ms = 0;
+    int64_t prof_rows = 0, prof_launches = 0;
+};
+
+extern "C" const char* bt_last_error(void) { return g_err.c_str(); }
+extern "C" int bt_version(void) { return 100; }
+
+static int ensure_rows(bt_ctx* c, size_t M, bool jac) {
+    if (M > c->rows_cap) {
+        if (c->rows) { cudaFree(c->rows); cudaFree(c->lf_rows); cudaFree(c->nl); cudaFree(c->logq); cudaFree(c->objc); }
+        const size_t cap = M + M / 8 + 1024;
+        CK(cudaMalloc(&c->rows, cap * c->D * sizeof(float)));
+        CK(cudaMalloc(&c->lf_rows, cap * c->L * sizeof(float)));
+        CK(cudaMalloc(&c->nl, cap * sizeof(float)));
+        CK(cudaMalloc(&c->logq, cap * sizeof(float)));
+        CK(cudaMalloc(&c->objc, cap * sizeof(float)));
+        c->rows_cap = cap;
+    }
+    if (jac && M > c->jac_cap) {
+        if (c->jac_rows) cudaFree(c->jac_rows);
+        const size_t cap = M + M / 8 + 1024;
+        CK(cudaMalloc(&c->jac_rows, cap * (size_t)(c->fm.T > 0 ? c->fm.T : 1) * c->L * sizeof(float)));
+        c->jac_cap = cap;
+    }
+    return 0;
+}
+
+extern "C" int bt_ctx_create(bt_ctx** out, int device, int N, int D, int L, int max_degree) {
+    REQUIRE(out, "null out pointer");
+    REQUIRE(N > 0 && D > 0 && D <= BT_MAX_D && L > 0 && L <= BT_MAX_L, "bad N/D/L");
+    REQUIRE(max_degree >= 0 && max_degree <= BT_MAX_DEGREE, "bad max_degree");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    bt_ctx* c = new bt_ctx();
+    c->device = device; c->N = N; c->D = D; c->L = L; c->max_degree = max_degree > 0 ? max_degree : 1;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    const size_t nd = (size_t)N * D;
+    CK(cudaMalloc(&c->theta, nd * 4)); CK(cudaMalloc(&c->v, nd * 4)); CK(cudaMalloc(&c->jt, nd * 4));
+    CK(cudaMalloc(&c->nll_lik, (size_t)N * 4)); CK(cudaMalloc(&c->grad_lik, nd * 4));
+    CK(cudaMalloc(&c->lf_cache, (size_t)N * L * 4));
+    CK(cudaMalloc(&c->accept, (size_t)N * 4)); CK(cudaMalloc(&c->logpa, (size_t)N * 4));
+    CK(cudaMalloc(&c->accepted_any, (size_t)N));
+    CK(cudaMalloc(&c->tmpf, (size_t)N * (size_t)(D * L > 64 ? D * L : 64) * 4));
+    CK(cudaMalloc(&c->tmpd, 64 * sizeof(double)));
+    CK(cudaMalloc(&c->owned_dev, (size_t)N));
+    CK(cudaMalloc(&c->nbr, (size_t)N * c->max_degree * 4));
+    CK(cudaMemset(c->nbr, 0xff, (size_t)N * c->max_degree * 4));
+    CK(cudaMemset(c->theta, 0, nd * 4)); CK(cudaMemset(c->v, 0, nd * 4)); CK(cudaMemset(c->jt, 0, nd * 4));
+    CK(cudaMemset(c->accept, 0, (size_t)N * 4)); CK(cudaMemset(c->logpa, 0, (size_t)N * 4));
+    CK(cudaMemset(c->accepted_any, 0, (size_t)N));
+    CK(cudaMemset(c->nll_lik, 0, (size_t)N * 4)); CK(cudaMemset(c->grad_lik, 0, nd * 4));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    memset(&c->pr, 0, sizeof c->pr);
+    *out = c;
+    return 0;
+}
+
+extern "C" int bt_ctx_destroy(bt_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->net_allocs) cudaFree(p);
+    tc_free(c->tc);
+    void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
+                    c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
+                    c->tmpf, c->tmpd, c->owned_dev};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return 0;
+}
+
+extern "C" int bt_set_stream(bt_ctx* c, uint64_t s) { REQUIRE(c, "null ctx"); c->stream = (cudaStream_t)s; return 0; }
+extern "C" int bt_set_mlp_mode(bt_ctx* c, int mode) {
+    REQUIRE(c, "null ctx");
+    REQUIRE(mode == BT_MLP_FP32 || mode == BT_MLP_BF16_TC, "unknown mlp mode");
+    if (mode == BT_MLP_BF16_TC) REQUIRE(c->tc.ready, "tensor-core weights not available (upload the network first)");
+    c->mlp_mode = mode;
+    return 0;
+}
+extern "C" int bt_synchronize(bt_ctx* c) { REQUIRE(c, "null ctx"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int64_t bt_kernel_launches(bt_ctx* c) { return c ? c->launches : -1; }
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& h, std::vector<void*>* track) {
+    CK(cudaMalloc(dst, h.size() * sizeof(T) + 16));
+    CK(cudaMemcpy(*dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (track) track->push_back(*dst);
+    return 0;
+}
+
+extern "C" int bt_upload_network(bt_ctx* c, int n_in, int order, int n_feat0, const int32_t* exponents,
+                                 const double* poly_means, const double* poly_stds, int n_blocks,
+                                 const int32_t* block_new, const double* const* weights,
+                                 const double* const* biases, const double* w_out, const double* b_out, int n_out) {
+    REQUIRE(c, "null ctx");
+    REQUIRE(n_blocks >= 0 && n_blocks <= BT_MAX_BLOCKS, "too many dense blocks");
+    REQUIRE(n_out == c->L, "network output count must equal L (restrict the last layer first)");
+    REQUIRE(n_in >= 1 && n_in <= BT_MAX_D, "bad n_in");
+    CK(cudaSetDevice(c->device));
+    for (void* p : c->net_allocs) cudaFree(p);
+    c->net_allocs.clear();
+    NetDev& net = c->net;
+    net.n_in = n_in; net.order = order; net.F0 = n_feat0; net.n_blocks = n_blocks; net.n_out = n_out;
+    std::vector<int> ex(exponents, exponents + (size_t)n_feat0 * order);
+    std::vector<float> mean(n_feat0), istd(n_feat0);
+    for (int f = 0; f < n_feat0; ++f) { mean[f] = (float)poly_means[f]; istd[f] = (float)(1.0 / poly_stds[f]); }
+    int* dex; float *dmean, *distd;
+    if (upload(&dex, ex, &c->net_allocs) || upload(&dmean, mean, &c->net_allocs) || upload(&distd, istd, &c->net_allocs)) return -1;
+    net.exps = dex; net.mean = dmean; net.inv_std = distd;
+    int w = n_feat0;
+    for (int l = 0; l < n_blocks; ++l) {
+        const int nw = block_new[l], ld = (nw + 7) / 8 * 8;
+        std::vector<float> wt((size_t)w * ld, 0.f), b(ld, 0.f);
+        for (int o = 0; o < nw; ++o) {
+            b[o] = (float)biases[l][o];
+            for (int k = 0; k < w; ++k) wt[(size_t)k * ld + o] = (float)weights[l][(size_t)o * w + k];
+        }
+        float *dw, *db;
+        if (upload(&dw, wt, &c->net_allocs) || upload(&db, b, &c->net_allocs)) return -1;
+        net.Wt[l] = dw; net.bias[l] = db; net.in_[l] = w; net.new_[l] = nw; net.ld[l] = ld;
+        w += nw;
+    }
+    net.F_total = w;
+    const double LOGE10 = log(10.0);
+    {
+        const int ld = (n_out + 7) / 8 * 8;
+        std::vector<float> wt((size_t)w * ld, 0.f);
+        for (int o = 0; o < n_out; ++o)
+            for (int k = 0; k < w; ++k) wt[(size_t)k * ld + o] = (float)(LOGE10 * w_out[(size_t)o * w + k]);
+        float* dw;
+        if (upload(&dw, wt, &c->net_allocs)) return -1;
+        net.Wt_out = dw; net.ld_out = ld;
+    }
+    c->shift.assign(n_out, 0.0);
+    for (int o = 0; o < n_out; ++o) c->shift[o] = LOGE10 * b_out[o];
+    c->have_net = true;
+    c->have_obs = false;   // observation constants depend on the shift
+    // tensor-core copy (bf16), best effort: fp32 path stays available if the shapes do not fit
+    tc_free(c->tc);
+    tc_build(c->tc, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, LOGE10);
+    return 0;
+}
+
+extern "C" int bt_upload_forward_map(bt_ctx* c, int d_full, const double* fixed, int d_sampling, const int32_t* idx) {
+    REQUIRE(c && c->have_net, "upload the network first");
+    REQUIRE(d_full == c->net.n_in + 1, "d_full must be n_in + 1 (kappa first)");
+    REQUIRE(d_sampling == c->D, "d_sampling must equal D");
+    FmapDev& fm = c->fm;
+    memset(&fm, 0, sizeof fm);
+    fm.D = d_sampling; fm.d_full = d_full; fm.T = 0;
+    for (int i = 0; i < d_full; ++i) fm.fixed[i] = (float)fixed[i];
+    for (int d = 0; d < BT_MAX_D; ++d) { fm.full_idx[d] = -1; fm.tslot[d] = -1; }
+    for (int d = 0; d < d_sampling; ++d) {
+        REQUIRE(idx[d] >= 0 && idx[d] < d_full, "sampled index out of range");
+        fm.full_idx[d] = idx[d];
+        fm.fixed[idx[d]] = 0.f;    // sampled entries start from 0 (neural_network_approx.py:189-192)
+        if (idx[d] >= 1) { REQUIRE(fm.T < BT_MAX_T, "too many sampled NN inputs"); fm.tslot[d] = fm.T; fm.tinput[fm.T] = idx[d] - 1; fm.T++; }
+    }
+    c->have_fm = true;
+    return 0;
+}
+
+extern "C" int bt_upload_observations(bt_ctx* c, const double* y, const double* sa, const double* sm,
+                                      const double* om, const double* fm1, const double* fp1) {
+    REQUIRE(c && c->have_net, "upload the network first (observation constants are centred on its output bias)");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->N * c->L;
+    std::vector<ObsConst> h(n);
+    for (size_t i = 0; i < n; ++i) {
+        const double sh = c->shift[i % c->L];
+        ObsConst& o = h[i];
+        REQUIRE(sa[i] > 0 && sm[i] > 0, "sigma_a and sigma_m must be positive");
+        o.lsa = (float)(log(sa[i]) - sh);
+        o.sm2 = (float)(sm[i] * sm[i]);
+        o.c = (float)expm1(sm[i] * sm[i]);
+        o.yr = (float)(y[i] / sa[i]);
+        o.ly = (float)(y[i] > 0 ? log(y[i]) - sh : NAN);
+        o.wr = (float)(om[i] / sa[i]);
+        o.lw = (float)(om[i] > 0 ? log(om[i]) - sh : NAN);
+        o.fm1 = (float)(fm1[i] - sh);
+        o.fp1 = (float)(fp1[i] - sh);
+        o.lsa0 = (float)log(sa[i]);
+        o.lsm = (float)log(sm[i]);
+        o.flags = (y[i] <= om[i] ? 1u : 0u) | (y[i] == om[i] ? 2u : 0u);
+    }
+    if (!c->obs) CK(cudaMalloc(&c->obs, n * sizeof(ObsConst)));
+    CK(cudaMemcpy(c->obs, h.data(), n * sizeof(ObsConst), cudaMemcpyHostToDevice));
+    c->have_obs = true;
+    return 0;
+}
+
+extern "C" int bt_upload_priors(bt_ctx* c, int has_spatial, const double* tau, const double* tau_init,
+                                int has_indicator, const double* lo, const double* hi, double delta) {
+    REQUIRE(c, "null ctx");
+    PriorDev& p = c->pr;
+    memset(&p, 0, sizeof p);
+    p.has_spatial = has_spatial; p.has_indicator = has_indicator;
+    for (int d = 0; d < c->D; ++d) {
+        if (has_spatial) { p.tau[d] = (float)tau[d]; p.tau_prop[d] = (float)fmin(tau[d], tau_init[d]); }
+        if (has_indicator) { p.lo[d] = (float)lo[d]; p.hi[d] = (float)hi[d]; }
+    }
+    if (has_indicator) { REQUIRE(delta > 0, "indicator margin must be positive"); p.inv_delta = (float)(1.0 / delta); p.g4 = (float)(4.0 / (delta * delta * delta * delta)); }
+    c->have_priors = true;
+    return 0;
+}
+
+extern "C" int bt_upload_graph(bt_ctx* c, const int32_t* nbr, int n_sites, const int32_t* site_sizes,
+                               const int32_t* site_pixels, const int64_t* global_id) {
+    REQUIRE(c, "null ctx");
+    REQUIRE(n_sites >= 1 && n_sites <= 1 << 20, "bad n_sites");
+    CK(cudaSetDevice(c->device));
+    if (nbr) CK(cudaMemcpy(c->nbr, nbr, (size_t)c->N * c->max_degree * 4, cudaMemcpyHostToDevice));
+    c->n_sites = n_sites;
+    c->site_size.assign(site_sizes, site_sizes + n_sites);
+    c->site_off.assign(n_sites + 1, 0);
+    for (int s = 0; s < n_sites; ++s) { REQUIRE(site_sizes[s] >= 0, "negative site size"); c->site_off[s + 1] = c->site_off[s] + site_sizes[s]; }
+    const int tot = c->site_off[n_sites];
+    REQUIRE(tot <= c->N, "sites hold more pixels than N");
+    for (int i = 0; i < tot; ++i) REQUIRE(site_pixels[i] >= 0 && site_pixels[i] < c->N, "site pixel out of range");
+    if (c->site_pix) cudaFree(c->site_pix);
+    CK(cudaMalloc(&c->site_pix, (size_t)(tot > 0 ? tot : 1) * 4));
+    CK(cudaMemcpy(c->site_pix, site_pixels, (size_t)tot * 4, cudaMemcpyHostToDevice));
+    if (c->gid) { cudaFree(c->gid); c->gid = nullptr; }
+    if (global_id) {
+        CK(cudaMalloc(&c->gid, (size_t)c->N * 8));
+        CK(cudaMemcpy(c->gid, global_id, (size_t)c->N * 8, cudaMemcpyHostToDevice));
+    }
+    c->have_graph = true;
+    return 0;
+}
+
+// ---- state ------------------------------------------------------------------------------------
+static int h2d_from_double(bt_ctx* c, float* dst, const double* src, size_t n) {
+    c->hf.resize(n);
+    for (size_t i = 0; i < n; ++i) c->hf[i] = (float)src[i];
+    CK(cudaMemcpyAsync(dst, c->hf.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int d2h_to_double(bt_ctx* c, double* dst, const float* src, size_t n) {
+    c->hf.resize(n);
+    CK(cudaMemcpyAsync(c->hf.data(), src, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) dst[i] = (double)c->hf[i];
+    return 0;
+}
+
+extern "C" int bt_set_state(bt_ctx* c, const double* theta, const double* v, const int32_t* j) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    const size_t nd = (size_t)c->N * c->D;
+    if (theta) { for (size_t i = 0; i < nd; ++i) REQUIRE(!isnan(theta[i]), "Theta contains NaN"); if (h2d_from_double(c, c->theta, theta, nd)) return -1; }
+    if (v && h2d_from_double(c, c->v, v, nd)) return -1;
+    if (j) { CK(cudaMemcpyAsync(c->jt, j, nd * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+extern "C" int bt_get_state(bt_ctx* c, double* theta, double* v, int32_t* j) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    const size_t nd = (size_t)c->N * c->D;
+    if (theta && d2h_to_double(c, theta, c->theta, nd)) return -1;
+    if (v && d2h_to_double(c, v, c->v, nd)) return -1;
+    if (j) { CK(cudaMemcpyAsync(j, c->jt, nd * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+extern "C" int bt_set_theta_f32(bt_ctx* c, const float* theta) {
+    REQUIRE(c && theta, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->theta, theta, (size_t)c->N * c->D * 4, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+extern "C" int bt_get_theta_f32(bt_ctx* c, float* theta) {
+    REQUIRE(c && theta, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(theta, c->theta, (size_t)c->N * c->D * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int bt_gather_theta_rows(bt_ctx* c, const int32_t* pix_dev, int n, float* out_dev) {
+    REQUIRE(c, "null ctx");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(c->device));
+    gather_rows_kernel<<<(n * c->D + 255) / 256, 256, 0, c->stream>>>(c->theta, pix_dev, n, c->D, out_dev);
+    KLAUNCH(c);
+    return 0;
+}
+extern "C" int bt_scatter_theta_rows(bt_ctx* c, const int32_t* pix_dev, int n, const float* in_dev) {
+    REQUIRE(c, "null ctx");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(c->device));
+    scatter_rows_kernel<<<(n * c->D + 255) / 256, 256, 0, c->stream>>>(c->theta, pix_dev, n, c->D, in_dev);
+    KLAUNCH(c);
+    return 0;
+}
+
+// ---- forward map dispatch ----------------------------------------------------------------------
+static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
+    if (M <= 0) return 0;
+    if (c->prof) CK(cudaEventRecord(c->ev0, c->stream));
+    if (c->mlp_mode == BT_MLP_BF16_TC) {
+        int rc = tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);
+        if (rc) return fail("tensor-core MLP launch failed", __FILE__, __LINE__);
+        KLAUNCH(c);
+    } else {
+        const size_t smem = ((size_t)c->net.F_total + BT_MAX_D + 1) * MLP_COLS * sizeof(float);
+        const int S = jac ? 1 + c->fm.T : 1, P = MLP_COLS / S;
+        const int tiles = (M + P - 1) / P;
+        const int grid = tiles < c->sm_count ? tiles : c->sm_count;
+        if (jac) {
+            CK(cudaFuncSetAttribute(mlp_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mlp_simt_kernel<true><<<grid, MLP_THREADS, smem, c->stream>>>(c->net, c->fm, rows, M, lf, jac);
+        } else {
+            CK(cudaFuncSetAttribute(mlp_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mlp_simt_kernel<false><<<grid, MLP_THREADS, smem, c->stream>>>(c->net, c->fm, rows, M, lf, jac);
+        }
+        KLAUNCH(c);
+    }
+    if (c->prof) {
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->prof_ms += ms; c->prof_rows += (int64_t)M * (jac ? 1 + c->fm.T : 1); c->prof_launches++;
+    }
+    return 0;
+}
+
+extern "C" int bt_mlp_profile(bt_ctx* c, int enable, int reset, double* ms, int64_t* rows, int64_t* launches) {
+    REQUIRE(c, "null ctx");
+    if (ms) *ms = c->prof_ms;
+    if (rows) *rows = c->prof_rows;
+    if (launches) *launches = c->prof_launches;
+    if (reset) { c->prof_ms = 0; c->prof_rows = 0; c->prof_launches = 0; }
+    c->prof = enable != 0;
+    return 0;
+}
+
+#define READY(c) REQUIRE((c) && (c)->have_net && (c)->have_fm && (c)->have_obs && (c)->have_graph && (c)->have_priors, \
+                         "context not fully configured (network, forward map, observations, priors, graph)")
+
+extern "C" int bt_compute_all(bt_ctx* c) {
+    READY(c);
+    CK(cudaSetDevice(c->device));
+    if (ensure_rows(c, c->N, true)) return -1;
+    if (run_mlp(c, c->theta, c->N, c->lf_rows, c->jac_rows)) return -1;
+    lik_all_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->fm, c->N, c->L, c->lf_rows, c->jac_rows, c->obs,
+                                                               c->nll_lik, c->grad_lik, c->lf_cache);
+    KLAUNCH(c);
+    return 0;
+}
+
+extern "C" int bt_init_v_from_grad(bt_ctx* c) {
+    READY(c);
+    CK(cudaSetDevice(c->device));
+    assemble_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->N, c->D, c->max_degree, c->theta, c->nbr,
+                                                                c->nll_lik, c->grad_lik, nullptr, nullptr, nullptr, c->v, c->jt);
+    KLAUNCH(c);
+    return 0;
+}
+
+extern "C" int bt_get_current(bt_ctx* c, double* log_f, double* nll_pix, double* grad_lik, double* obj_chrom,
+                              double* obj_glob, double* grad) {
+    READY(c);
+    CK(cudaSetDevice(c->device));
+    const size_t N = c->N, D = c->D, L = c->L;
+    if (log_f) {
+        if (d2h_to_double(c, log_f, c->lf_cache, N * L)) return -1;
+        for (size_t i = 0; i < N * L; ++i) log_f[i] += c->shift[i % L];
+    }
+    if (nll_pix && d2h_to_double(c, nll_pix, c->nll_lik, N)) return -1;
+    if (grad_lik && d2h_to_double(c, grad_lik, c->grad_lik, N * D)) return -1;
+    if (obj_chrom || obj_glob || grad) {
+        float* oc = c->tmpf; float* og = c->tmpf + N; float* g = c->tmpf + 2 * N;
+        assemble_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->N, c->D, c->max_degree, c->theta, c->nbr,
+                                                                    c->nll_lik, c->grad_lik, oc, og, g, nullptr, nullptr);
+        KLAUNCH(c);
+        if (obj_chrom && d2h_to_double(c, obj_chrom, oc, N)) return -1;
+        if (obj_glob && d2h_to_double(c, obj_glob, og, N)) return -1;
+        if (grad && d2h_to_double(c, grad, g, N * D)) return -1;
+    }
+    return 0;
+}
+
+static int upload_owned(bt_ctx* c, const uint8_t* owned, const uint8_t** dev) {
+    *dev = nullptr;
+    if (owned) {
+        CK(cudaMemcpyAsync(c->owned_dev, owned, c->N, cudaMemcpyHostToDevice, c->stream));
+        *dev = c->owned_dev;
+    }
+    return 0;
+}
+
+extern "C" int bt_objective_terms(bt_ctx* c, const uint8_t* owned, double* out) {
+    READY(c);
+    REQUIRE(out, "null out");
+    CK(cudaSetDevice(c->device));
+    const uint8_t* od;
+    if (upload_owned(c, owned, &od)) return -1;
+    const int nq = 1 + 2 * c->D;
+    CK(cudaMemsetAsync(c->tmpd, 0, 64 * sizeof(double), c->stream));
+    objective_terms_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->N, c->D, c->max_degree, c->theta, c->nbr,
+                                                                       c->nll_lik, od, c->tmpd);
+    KLAUNCH(c);
+    CK(cudaMemcpyAsync(out, c->tmpd, nq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double tot = 0;
+    for (int q = 0; q < nq; ++q) tot += out[q];
+    out[nq] = tot;
+    return 0;
+}
+
+extern "C" int bt_forward_map(bt_ctx* c, int M, const double* theta, double* log_f, double* grad_log_f) {
+    REQUIRE(c && c->have_net && c->have_fm, "upload the network and forward map first");
+    REQUIRE(M > 0 && theta && log_f, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    if (ensure_rows(c, M, grad_log_f != nullptr)) return -1;
+    const size_t D = c->D, L = c->L, T = c->fm.T;
+    if (h2d_from_double(c, c->rows, theta, (size_t)M * D)) return -1;
+    if (run_mlp(c, c->rows, M, c->lf_rows, grad_log_f ? c->jac_rows : nullptr)) return -1;
+    if (d2h_to_double(c, log_f, c->lf_rows, (size_t)M * L)) return -1;
+    for (size_t i = 0; i < (size_t)M * L; ++i) log_f[i] += c->shift[i % L];
+    if (grad_log_f) {
+        std::vector<double> jac((size_t)M * (T > 0 ? T : 1) * L);
+        if (T > 0 && d2h_to_double(c, jac.data(), c->jac_rows, (size_t)M * T * L)) return -1;
+        for (size_t m = 0; m < (size_t)M; ++m)
+            for (size_t d = 0; d < D; ++d)
+                for (size_t l = 0; l < L; ++l)
+                    grad_log_f[(m * D + d) * L + l] = c->fm.tslot[d] < 0 ? 1.0 : jac[(m * T + c->fm.tslot[d]) * L + l];
+    }
+    return 0;
+}
+
+// ---- transition kernels --------------------------------------------------------------------------
+extern "C" int bt_begin_iteration(bt_ctx* c) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->accept, 0, (size_t)c->N * 4, c->stream));
+    CK(cudaMemsetAsync(c->logpa, 0, (size_t)c->N * 4, c->stream));
+    return 0;
+}
+
+static int stage_inject(bt_ctx* c, const float* host, size_t n, float** dev_out, std::vector<void*>& tmp) {
+    *dev_out = nullptr;
+    if (!host) return 0;
+    float* d;
+    CK(cudaMalloc(&d, n * sizeof(float)));
+    tmp.push_back(d);
+    CK(cudaMemcpyAsync(d, host, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    *dev_out = d;
+    return 0;
+}
+static void free_tmp(bt_ctx* c, std::vector<void*>& tmp) {
+    if (tmp.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (void* p : tmp) cudaFree(p);
+    tmp.clear();
+}
+
+extern "C" int bt_pmala_site(bt_ctx* c, int site, double eps, double eta, double alpha, uint64_t seed, int64_t t,
+                             const float* z_inject, const float* u_inject) {
+    READY(c);
+    REQUIRE(site >= 0 && site < c->n_sites, "no such site");
+    CK(cudaSetDevice(c->device));
+    const int n_pix = c->site_size[site];
+    if (n_pix == 0) return 0;
+    const int* sp = c->site_pix + c->site_off[site];
+    if (ensure_rows(c, n_pix, true)) return -1;
+    std::vector<void*> tmp;
+    float *zd, *ud;
+    if (stage_inject(c, z_inject, (size_t)c->N * c->D, &zd, tmp) || stage_inject(c, u_inject, c->N, &ud, tmp)) { free_tmp(c, tmp); return -1; }
+    const int chromatic = c->n_sites > 1;
+    pmala_propose_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(c->pr, n_pix, sp, c->D, c->max_degree, c->theta, c->nbr,
+        c->nll_lik, c->grad_lik, c->v, (float)eps, (float)eta, chromatic, seed, t, site, c->gid, zd, c->rows, c->logq, c->objc);
+    KLAUNCH(c);
+    if (run_mlp(c, c->rows, n_pix, c->lf_rows, c->jac_rows)) { free_tmp(c, tmp); return -1; }
+    pmala_accept_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, n_pix, sp, c->D, c->L, c->max_degree,
+        c->theta, c->nbr, c->obs, c->nll_lik, c->grad_lik, c->lf_cache, c->v, c->jt, c->rows, c->lf_rows, c->jac_rows,
+        c->logq, c->objc, (float)eps, (float)eta, (float)alpha, chromatic, seed, t, site, c->gid, ud, c->accept, c->logpa);
+    KLAUNCH(c);
+    free_tmp(c, tmp);
+    return 0;
+}
+
+extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t, const float* cand_inject,
+                           const float* usel_inject, const float* uacc_inject) {
+    READY(c);
+    REQUIRE(site >= 0 && site < c->n_sites, "no such site");
+    REQUIRE(K >= 1, "k_mtm must be >= 1");
+    REQUIRE(c->pr.has_indicator, "The Posterior has no specified smooth indicator prior");   // my_sampler.py:132-133
+    REQUIRE(c->pr.has_spatial || cand_inject, "MTM without a spatial prior needs injected proposals (not on the GPU path)");
+    CK(cudaSetDevice(c->device));
+    const int n_pix = c->site_size[site];
+    if (n_pix == 0) return 0;
+    const int* sp = c->site_pix + c->site_off[site];
+    const size_t M = (size_t)n_pix * (K + 1);
+    REQUIRE(M < (size_t)1 << 31, "too many candidate rows for one launch");
+    if (ensure_rows(c, M, false)) return -1;
+    std::vector<void*> tmp;
+    float *cd, *usd, *uad;
+    if (stage_inject(c, cand_inject, (size_t)c->N * K * c->D, &cd, tmp) || stage_inject(c, usel_inject, c->N, &usd, tmp) ||
+        stage_inject(c, uacc_inject, c->N, &uad, tmp)) { free_tmp(c, tmp); return -1; }
+    mtm_gen_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->pr, n_pix, sp, c->D, K, c->max_degree, c->theta,
+        c->nbr, seed, t, site, c->gid, cd, c->rows);
+    KLAUNCH(c);
+    if (run_mlp(c, c->rows, (int)M, c->lf_rows, nullptr)) { free_tmp(c, tmp); return -1; }
+    const int warps_per_block = 4;
+    mtm_select_kernel<<<(n_pix + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, c->stream>>>(c->pr, c->fm,
+        n_pix, sp, c->D, c->L, K, c->max_degree, c->n_sites > 1, c->theta, c->nbr, c->obs, c->jt, c->rows, c->lf_rows, c->nl,
+        seed, t, site, c->gid, usd, uad, c->accept, c->logpa, c->accepted_any);
+    KLAUNCH(c);
+    free_tmp(c, tmp);
+    return 0;
+}
+
+extern "C" int bt_mtm_finish(bt_ctx* c, double alpha) {
+    READY(c);
+    CK(cudaSetDevice(c->device));
+    if (ensure_rows(c, c->N, true)) return -1;
+    if (run_mlp(c, c->theta, c->N, c->lf_rows, c->jac_rows)) return -1;
+    mtm_finish_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, c->N, c->D, c->L, c->max_degree, c->theta,
+        c->nbr, c->obs, c->lf_rows, c->jac_rows, c->nll_lik, c->grad_lik, c->lf_cache, c->v, (float)alpha, c->accepted_any);
+    KLAUNCH(c);
+    return 0;
+}
+
+extern "C" int bt_get_step_stats(bt_ctx* c, double* accept, double* log_proba) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (accept && d2h_to_double(c, accept, c->accept, c->N)) return -1;
+    if (log_proba && d2h_to_double(c, log_proba, c->logpa, c->N)) return -1;
+    return 0;
+}
+
+extern "C" int bt_reduce_step_stats(bt_ctx* c, const uint8_t* owned, double* out) {
+    REQUIRE(c && out, "null argument");
+    CK(cudaSetDevice(c->device));
+    const uint8_t* od;
+    if (upload_owned(c, owned, &od)) return -1;
+    CK(cudaMemsetAsync(c->tmpd, 0, 2 * sizeof(double), c->stream));
+    reduce_stats_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, c->accept, c->logpa, od, c->tmpd);
+    KLAUNCH(c);
+    CK(cudaMemcpyAsync(out, c->tmpd, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- debug: expose the Philox draws -------------------------------------------------------------
+extern "C" int bt_debug_philox_pmala(bt_ctx* c, int site, uint64_t seed, int64_t t, float* z_out, float* u_out) {
+    READY(c);
+    REQUIRE(site >= 0 && site < c->n_sites && z_out && u_out, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    const int n_pix = c->site_size[site];
+    float *zd, *ud;
+    CK(cudaMalloc(&zd, (size_t)c->N * c->D * 4)); CK(cudaMalloc(&ud, (size_t)c->N * 4));
+    CK(cudaMemsetAsync(zd, 0, (size_t)c->N * c->D * 4, c->stream)); CK(cudaMemsetAsync(ud, 0, (size_t)c->N * 4, c->stream));
+    if (n_pix > 0) {
+        debug_pmala_noise_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(n_pix, c->site_pix + c->site_off[site], c->D, seed, t, site, c->gid, zd, ud);
+        KLAUNCH(c);
+    }
+    CK(cudaMemcpyAsync(z_out, zd, (size_t)c->N * c->D * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(u_out, ud, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(zd); cudaFree(ud);
+    return 0;
+}
+
+extern "C" int bt_debug_philox_mtm(bt_ctx* c, int site, int K, uint64_t seed, int64_t t, float* cand_out,
+                                   float* usel_out, float* uacc_out) {
+    READY(c);
+    REQUIRE(site >= 0 && site < c->n_sites && cand_out && usel_out && uacc_out && K >= 1, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    const int n_pix = c->site_size[site];
+    const size_t M = (size_t)n_pix * (K + 1);
+    if (ensure_rows(c, M, false)) return -1;
+    float *cd, *usd, *uad;
+    const size_t nc = (size_t)c->N * K * c->D;
+    CK(cudaMalloc(&cd, nc * 4)); CK(cudaMalloc(&usd, (size_t)c->N * 4)); CK(cudaMalloc(&uad, (size_t)c->N * 4));
+    CK(cudaMemsetAsync(cd, 0, nc * 4, c->stream));
+    CK(cudaMemsetAsync(usd, 0, (size_t)c->N * 4, c->stream)); CK(cudaMemsetAsync(uad, 0, (size_t)c->N * 4, c->stream));
+    if (n_pix > 0) {
+        const int* sp = c->site_pix + c->site_off[site];
+        mtm_gen_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->pr, n_pix, sp, c->D, K, c->max_degree, c->theta,
+            c->nbr, seed, t, site, c->gid, nullptr, c->rows);
+        KLAUNCH(c);
+        const long long tot = (long long)n_pix * K * c->D;
+        debug_scatter_cand_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(n_pix, sp, c->D, K, c->rows, cd);
+        KLAUNCH(c);
+        debug_mtm_u_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(n_pix, sp, seed, t, site, c->gid, usd, uad);
+        KLAUNCH(c);
+    }
+    CK(cudaMemcpyAsync(cand_out, cd, nc * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(usel_out, usd, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(uacc_out, uad, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(cd); cudaFree(usd); cudaFree(uad);
+    return 0;
+}

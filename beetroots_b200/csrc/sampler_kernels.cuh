@@ -1,0 +1,564 @@
+// Likelihood / prior / sampler-update kernels (float32, HBM-bound, one thread or one warp per
+// pixel).  Replaces, per colour class, the bodies of
+//   MySampler.generate_new_sample_pmala_rmsprop  (sampler/my_sampler.py:752-903)
+//   MySampler.generate_new_sample_mtm            (sampler/my_sampler.py:1006-1197)
+// and the pieces of Posterior.compute_all they call (modelling/posterior.py:332-446).
+#pragma once
+#include "common.cuh"
+#include "mlp_simt.cuh"
+
+struct PriorDev {
+    int has_spatial, has_indicator;
+    float tau[BT_MAX_D];        // prior_spatial.weights
+    float tau_prop[BT_MAX_D];   // min(initial_weights, weights)  (my_sampler.py:149-152, 1097-1100)
+    float lo[BT_MAX_D], hi[BT_MAX_D];
+    float inv_delta;            // 1 / indicator_margin_scale
+    float g4;                   // 4 / delta^4
+};
+
+// ---- priors -------------------------------------------------------------------------------
+// sum over the neighbour set V_n of (x_d - theta_id)^2 and (x_d - theta_id)
+// (l22_discrete_grad_prior.py:9-80 evaluated through the neighbour table)
+__device__ __forceinline__ void neighbour_sums(const float* __restrict__ theta, const int* __restrict__ nbr_n,
+                                               int max_degree, int D, const float (&x)[BT_MAX_D],
+                                               float (&had)[BT_MAX_D], float (&lap)[BT_MAX_D]) {
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) had[d] = lap[d] = 0.f;
+    for (int j = 0; j < max_degree; ++j) {
+        const int m = nbr_n[j];
+        if (m < 0) continue;
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d)
+            if (d < D) {
+                const float diff = x[d] - theta[(size_t)m * D + d];
+                had[d] = fmaf(diff, diff, had[d]);
+                lap[d] += diff;
+            }
+    }
+}
+
+// smooth indicator: penalty (smooth_indicator_prior.py:35-54) and gradient (:57-82)
+__device__ __forceinline__ float indicator_terms(const PriorDev& pr, int D, const float (&x)[BT_MAX_D],
+                                                 float (&g)[BT_MAX_D]) {
+    float pen = 0.f;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) {
+        g[d] = 0.f;
+        if (d < D) {
+            float dist = 0.f;
+            if (x[d] > pr.hi[d]) dist = x[d] - pr.hi[d];
+            else if (x[d] < pr.lo[d]) dist = x[d] - pr.lo[d];
+            const float sc = fabsf(dist) * pr.inv_delta;
+            const float sc2 = sc * sc;
+            pen += sc2 * sc2;
+            g[d] = pr.g4 * dist * dist * dist;
+        }
+    }
+    return pen;
+}
+
+// prior part of the per-pixel objective (chromatic convention, factor 1) and of the gradient
+__device__ __forceinline__ float prior_eval(const PriorDev& pr, const float* __restrict__ theta,
+                                            const int* __restrict__ nbr_n, int max_degree, int D,
+                                            const float (&x)[BT_MAX_D], float (&grad)[BT_MAX_D],
+                                            float* spatial_out = nullptr) {
+    float obj = 0.f, sp = 0.f;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) grad[d] = 0.f;
+    if (pr.has_spatial) {
+        float had[BT_MAX_D], lap[BT_MAX_D];
+        neighbour_sums(theta, nbr_n, max_degree, D, x, had, lap);
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d)
+            if (d < D) {
+                sp = fmaf(pr.tau[d], had[d], sp);                 // l22:107,125-128 (chromatic)
+                grad[d] = 2.f * pr.tau[d] * lap[d];               // l22:137-139
+            }
+        obj += sp;
+    }
+    if (spatial_out) *spatial_out = sp;
+    if (pr.has_indicator) {
+        float gi[BT_MAX_D];
+        obj += indicator_terms(pr, D, x, gi);
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) grad[d] += gi[d];
+    }
+    return obj;
+}
+
+// likelihood of one row: nll and (optionally) gradient wrt the sampled dims
+template <bool WITH_GRAD>
+__device__ __forceinline__ float lik_row(const FmapDev& fm, int L, const float* __restrict__ lf_row,
+                                         const float* __restrict__ jac_row, const ObsConst* __restrict__ obs_n,
+                                         float (&grad)[BT_MAX_D]) {
+    float nll = 0.f;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) grad[d] = 0.f;
+    for (int l = 0; l < L; ++l) {
+        const float4* op = reinterpret_cast<const float4*>(obs_n + l);
+        union { float4 v[3]; ObsConst o; } u;
+        u.v[0] = __ldg(op); u.v[1] = __ldg(op + 1); u.v[2] = __ldg(op + 2);
+        float v, G;
+        mixing_line<WITH_GRAD>(lf_row[l], u.o, v, G);
+        nll += v;                                                    // :568
+        if (WITH_GRAD) {
+#pragma unroll
+            for (int d = 0; d < BT_MAX_D; ++d)
+                if (d < fm.D) {
+                    const float J = (fm.tslot[d] < 0) ? 1.0f : jac_row[fm.tslot[d] * L + l];
+                    grad[d] += nan_to_num(G * J);                    // :673-674
+                }
+        }
+    }
+    return nll;
+}
+
+// ---- compute_all: likelihood terms of every pixel from (lf, jac) --------------------------
+__global__ void lik_all_kernel(FmapDev fm, int N, int L, const float* __restrict__ lf_rows,
+                               const float* __restrict__ jac_rows, const ObsConst* __restrict__ obs,
+                               float* __restrict__ nll_lik, float* __restrict__ grad_lik, float* __restrict__ lf_cache) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float g[BT_MAX_D];
+    const float nll = lik_row<true>(fm, L, lf_rows + (size_t)n * L, jac_rows + (size_t)n * fm.T * L,
+                                    obs + (size_t)n * L, g);
+    nll_lik[n] = nll;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < fm.D) grad_lik[(size_t)n * fm.D + d] = g[d];
+    if (lf_cache != lf_rows)
+        for (int l = 0; l < L; ++l) lf_cache[(size_t)n * L + l] = lf_rows[(size_t)n * L + l];
+}
+
+// objective / gradient assembly for bt_get_current and bt_init_v_from_grad (posterior.py:402-446, 212-241)
+__global__ void assemble_kernel(PriorDev pr, int N, int D, int max_degree, const float* __restrict__ theta,
+                                const int* __restrict__ nbr, const float* __restrict__ nll_lik,
+                                const float* __restrict__ grad_lik, float* __restrict__ obj_chrom,
+                                float* __restrict__ obj_glob, float* __restrict__ grad, float* __restrict__ v_init,
+                                int* __restrict__ j_init) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float x[BT_MAX_D], gp[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? theta[(size_t)n * D + d] : 0.f;
+    float sp;
+    const float pobj = prior_eval(pr, theta, nbr + (size_t)n * max_degree, max_degree, D, x, gp, &sp);
+    if (obj_chrom) obj_chrom[n] = nll_lik[n] + pobj;
+    if (obj_glob) obj_glob[n] = nll_lik[n] + pobj - 0.5f * sp;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) {
+            const float g = nan_to_num(grad_lik[(size_t)n * D + d] + gp[d]);
+            if (grad) grad[(size_t)n * D + d] = g;
+            if (v_init) v_init[(size_t)n * D + d] = g * g;
+            if (j_init) j_init[(size_t)n * D + d] = 0;
+        }
+}
+
+// ---- PMALA ---------------------------------------------------------------------------------
+// propose (my_sampler.py:756-808): one thread per pixel of the colour class
+__global__ void pmala_propose_kernel(PriorDev pr, int n_pix, const int* __restrict__ site_pix, int D, int max_degree,
+                                     const float* __restrict__ theta, const int* __restrict__ nbr,
+                                     const float* __restrict__ nll_lik, const float* __restrict__ grad_lik,
+                                     const float* __restrict__ v, float eps, float eta, int chromatic,
+                                     uint64_t seed, int64_t t, int site, const int64_t* __restrict__ gid,
+                                     const float* __restrict__ z_inject,
+                                     float* __restrict__ cand_rows, float* __restrict__ logq_fwd,
+                                     float* __restrict__ obj_cur) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const int n = site_pix[i];
+    float x[BT_MAX_D], gp[BT_MAX_D], z[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? theta[(size_t)n * D + d] : 0.f;
+    float sp;
+    const float pobj = prior_eval(pr, theta, nbr + (size_t)n * max_degree, max_degree, D, x, gp, &sp);
+    obj_cur[i] = nll_lik[n] + pobj - (chromatic ? 0.f : 0.5f * sp);       // :745-750, :857
+    if (z_inject) {
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) z[d] = (d < D) ? z_inject[(size_t)n * D + d] : 0.f;
+    } else {
+        bt_normals(z, D, seed, t, BT_PURPOSE_PMALA_Z, site, gid ? gid[n] : (int64_t)n, 0u);
+    }
+    float lq = 0.f;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) {
+            const float g = nan_to_num(grad_lik[(size_t)n * D + d] + gp[d]);     // posterior.py:240
+            const float G = 1.0f / (eta + sqrtf(v[(size_t)n * D + d]));          // :761
+            const float zs = z[d] * sqrtf(eps * G);                             // :768
+            const float mu = x[d] - 0.5f * eps * G * g;                          // :796-800
+            const float c = mu + zs;                                             // :802
+            const float dc = c - mu;
+            lq += -0.5f * logf(G) - dc * dc / (2.0f * eps * G);                  // :804-808
+            cand_rows[(size_t)i * D + d] = c;
+        }
+    logq_fwd[i] = lq;
+}
+
+// accept / reject and state update (my_sampler.py:822-896)
+__global__ void pmala_accept_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_pix, int D, int L,
+                                    int max_degree, float* __restrict__ theta, const int* __restrict__ nbr,
+                                    const ObsConst* __restrict__ obs, float* __restrict__ nll_lik,
+                                    float* __restrict__ grad_lik, float* __restrict__ lf_cache,
+                                    float* __restrict__ v, int* __restrict__ jt,
+                                    const float* __restrict__ cand_rows, const float* __restrict__ lf_rows,
+                                    const float* __restrict__ jac_rows, const float* __restrict__ logq_fwd,
+                                    const float* __restrict__ obj_cur, float eps, float eta, float alpha,
+                                    int chromatic, uint64_t seed, int64_t t, int site,
+                                    const int64_t* __restrict__ gid, const float* __restrict__ u_inject,
+                                    float* __restrict__ accept, float* __restrict__ logpa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const int n = site_pix[i];
+    float c[BT_MAX_D], gp[BT_MAX_D], gl[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) c[d] = (d < D) ? cand_rows[(size_t)i * D + d] : 0.f;
+    const float nll_c = lik_row<true>(fm, L, lf_rows + (size_t)i * L, jac_rows + (size_t)i * fm.T * L,
+                                      obs + (size_t)n * L, gl);
+    float sp;
+    const float pobj = prior_eval(pr, theta, nbr + (size_t)n * max_degree, max_degree, D, c, gp, &sp);
+    const float obj_c = nll_c + pobj - (chromatic ? 0.f : 0.5f * sp);
+    float lq = 0.f;
+    float vnew[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) {
+            const float g = nan_to_num(gl[d] + gp[d]);
+            const float vc = alpha * v[(size_t)n * D + d] + (1.0f - alpha) * g * g;   // :823-825
+            const float G = 1.0f / (eta + sqrtf(vc));                                 // :826
+            const float mu = c[d] - 0.5f * eps * G * g;                               // :841-845
+            const float dc = theta[(size_t)n * D + d] - mu;
+            lq += -0.5f * logf(G) - dc * dc / (2.0f * eps * G);                       // :847-851
+            vnew[d] = vc;
+        }
+    const float lpa = -obj_c + obj_cur[i] + lq - logq_fwd[i];                         // :865-870
+    const float u = u_inject ? u_inject[n] : bt_uniform(seed, t, BT_PURPOSE_PMALA_U, site, gid ? gid[n] : (int64_t)n);
+    const bool acc = logf(u) < lpa;                                                   // :873-874
+    accept[n] = acc ? 1.f : 0.f;
+    logpa[n] = lpa;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) {
+            v[(size_t)n * D + d] = vnew[d];                                           // :886-888 (always)
+            jt[(size_t)n * D + d] = acc ? 0 : jt[(size_t)n * D + d] + 1;              // :890-896
+            if (acc) {
+                theta[(size_t)n * D + d] = c[d];                                      // :876-880
+                grad_lik[(size_t)n * D + d] = gl[d];
+            }
+        }
+    if (acc) {
+        nll_lik[n] = nll_c;
+        for (int l = 0; l < L; ++l) lf_cache[(size_t)n * L + l] = lf_rows[(size_t)i * L + l];
+    }
+}
+
+// ---- MTM -----------------------------------------------------------------------------------
+// candidate generation (sampler/utils/utils.py:274-349): thread per (pixel, k); slot K = current value
+__global__ void mtm_gen_kernel(PriorDev pr, int n_pix, const int* __restrict__ site_pix, int D, int K, int max_degree,
+                               const float* __restrict__ theta, const int* __restrict__ nbr, uint64_t seed,
+                               int64_t t, int site, const int64_t* __restrict__ gid,
+                               const float* __restrict__ cand_inject, float* __restrict__ cand_rows) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_pix * (K + 1)) return;
+    const int i = (int)(idx / (K + 1)), k = (int)(idx - (long long)i * (K + 1));
+    const int n = site_pix[i];
+    float* out = cand_rows + (size_t)idx * D;
+    if (k == K) {                                                                     // my_sampler.py:1011-1015
+        for (int d = 0; d < D; ++d) out[d] = theta[(size_t)n * D + d];
+        return;
+    }
+    if (cand_inject) {
+        for (int d = 0; d < D; ++d) out[d] = cand_inject[((size_t)n * K + k) * D + d];
+        return;
+    }
+    const int* nb = nbr + (size_t)n * max_degree;
+    int deg = 0;
+    for (int j = 0; j < max_degree; ++j) deg += (nb[j] >= 0);
+    if (deg == 0) {                                                                   // utils.py:321-322: zeros
+        for (int d = 0; d < D; ++d) out[d] = 0.f;
+        return;
+    }
+    const int64_t g = gid ? gid[n] : (int64_t)n;
+    uint32_t r[4];
+    bt_philox(r, seed, t, BT_PURPOSE_MTM_SUBSET, site, g, (uint32_t)k);
+    // uniform over the 2^deg - 1 non-empty subsets (= Bernoulli(1/2) per neighbour, redrawn while empty, :326-328)
+    const uint32_t mask = 1u + (uint32_t)(((uint64_t)r[0] * (uint64_t)((1u << deg) - 1u)) >> 32);
+    float mean[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) mean[d] = 0.f;
+    int m = 0, slot = 0;
+    for (int j = 0; j < max_degree; ++j) {
+        if (nb[j] < 0) continue;
+        if ((mask >> slot) & 1u) {
+            ++m;
+#pragma unroll
+            for (int d = 0; d < BT_MAX_D; ++d)
+                if (d < D) mean[d] += theta[(size_t)nb[j] * D + d];
+        }
+        ++slot;
+    }
+    float z[BT_MAX_D];
+    bt_normals(z, D, seed, t, BT_PURPOSE_MTM_Z, site, g, (uint32_t)k);
+    const float inv_m = 1.0f / (float)m;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) out[d] = mean[d] * inv_m + z[d] * inv_m * rsqrtf(pr.tau_prop[d]);  // :336-345
+}
+
+// proposal log-density of one candidate (utils.py:419-495): sum_d log sum_S sqrt(tau_d) m exp(-(x_d-mu_Sd)^2 tau_d m^2)
+__device__ __forceinline__ float proposal_log_density(const PriorDev& pr, int D, int deg, const float (&nbv)[BT_MAX_DEGREE][BT_MAX_D],
+                                                      const float (&x)[BT_MAX_D]) {
+    float total = 0.f;
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) {
+        if (d >= D) continue;
+        const float tau = pr.tau_prop[d], st = sqrtf(tau);
+        // pass 1: max exponent, pass 2: weighted sum (numba_logsumexp_stable, utils.py:390-416)
+        float mx = -INFINITY;
+        for (uint32_t mask = 1; mask < (1u << deg); ++mask) {
+            float sum = 0.f;
+            int m = 0;
+            for (int j = 0; j < deg; ++j)
+                if ((mask >> j) & 1u) { sum += nbv[j][d]; ++m; }
+            const float diff = x[d] - sum / (float)m;
+            mx = fmaxf(mx, -diff * diff * tau * (float)(m * m));
+        }
+        float acc = 0.f;
+        for (uint32_t mask = 1; mask < (1u << deg); ++mask) {
+            float sum = 0.f;
+            int m = 0;
+            for (int j = 0; j < deg; ++j)
+                if ((mask >> j) & 1u) { sum += nbv[j][d]; ++m; }
+            const float diff = x[d] - sum / (float)m;
+            acc += st * (float)m * expf(-diff * diff * tau * (float)(m * m) - mx);
+        }
+        total += logf(acc) + mx;
+    }
+    return total;
+}
+
+// weights, selection, accept (my_sampler.py:1017-1178): one warp per pixel, lanes stride over candidates
+__global__ void mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_pix, int D, int L,
+                                  int K, int max_degree, int chromatic, float* __restrict__ theta,
+                                  const int* __restrict__ nbr, const ObsConst* __restrict__ obs,
+                                  int* __restrict__ jt, const float* __restrict__ cand_rows,
+                                  const float* __restrict__ lf_rows, float* __restrict__ nl_scratch,
+                                  uint64_t seed, int64_t t, int site, const int64_t* __restrict__ gid,
+                                  const float* __restrict__ usel_inject, const float* __restrict__ uacc_inject,
+                                  float* __restrict__ accept, float* __restrict__ logpa, uint8_t* __restrict__ accepted_any) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= n_pix) return;
+    const int i = warp_global, n = site_pix[i];
+    const int K1 = K + 1;
+    const int* nb = nbr + (size_t)n * max_degree;
+    float nbv[BT_MAX_DEGREE][BT_MAX_D];
+    int deg = 0;
+    for (int j = 0; j < max_degree; ++j) {
+        const int m = nb[j];
+        if (m < 0) continue;
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) nbv[deg][d] = (d < D) ? theta[(size_t)m * D + d] : 0.f;
+        ++deg;
+    }
+    float* nl = nl_scratch + (size_t)i * K1;
+    // ---- negative log weight of every candidate
+    float mn = INFINITY;
+    for (int k = lane; k < K1; k += 32) {
+        const size_t row = (size_t)i * K1 + k;
+        float x[BT_MAX_D], dummy[BT_MAX_D];
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[row * D + d] : 0.f;
+        float val = lik_row<false>(fm, L, lf_rows + row * L, nullptr, obs + (size_t)n * L, dummy);  // :1021-1025
+        if (pr.has_spatial) {                                                                      // posterior.py:96-103
+            float sp = 0.f;
+            for (int j = 0; j < deg; ++j)
+#pragma unroll
+                for (int d = 0; d < BT_MAX_D; ++d)
+                    if (d < D) { const float df = x[d] - nbv[j][d]; sp = fmaf(pr.tau[d] * df, df, sp); }
+            val += sp;   // a colour class never holds all N pixels -> chromatic factor 1 (l22:103-105)
+        }
+        if (pr.has_indicator) val += indicator_terms(pr, D, x, dummy);                             // posterior.py:105-110
+        if (pr.has_spatial) val += proposal_log_density(pr, D, deg, nbv, x);                       // my_sampler.py:1093-1105
+        nl[k] = val;
+        mn = fminf(mn, val);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    __syncwarp();
+    // ---- lane 0: selection, ratio, accept.  The reference works with w_k = exp(-(nl_k - min nl))
+    // in float64 (:1107-1114); float32 would flush w_k to 0 beyond 87 nats, so everything is done
+    // in the log domain, relative to the best proposal (numerator, selection) and to the best
+    // remaining candidate (denominator).  A weight is dropped when float64 would have underflowed
+    // (nl_k - min > 745.13), which reproduces the reference's non-finite -> accepted quirk (:1156-1159).
+    if (lane == 0) {
+        const int64_t g = gid ? gid[n] : (int64_t)n;
+        const float F64_UNDERFLOW = 745.13f;
+        float dp = INFINITY;                                         // best proposal, relative to the global min
+        for (int k = 0; k < K; ++k) dp = fminf(dp, nl[k] - mn);
+        float s_prop = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float dk = nl[k] - mn;
+            if (dk <= F64_UNDERFLOW) s_prop += expf(-(dk - dp));
+        }
+        const float log_num = (s_prop > 0.f) ? logf(s_prop) - dp : -INFINITY;          // :1114
+        // inverse-CDF selection with one uniform: Generator.choice == searchsorted(cdf, u, 'right') (:1123-1131)
+        const float us = usel_inject ? usel_inject[n] : bt_uniform(seed, t, BT_PURPOSE_MTM_USEL, site, g);
+        float s_all = 0.f;                                           // softmax never underflows to all-zero (own max)
+        for (int k = 0; k < K; ++k) s_all += expf(-((nl[k] - mn) - dp));
+        const float target = us * s_all;
+        float cum = 0.f;
+        int sel = K - 1;
+        for (int k = 0; k < K; ++k) {
+            cum += expf(-((nl[k] - mn) - dp));
+            if (cum > target) { sel = k; break; }
+        }
+        // denominator: sum over all candidates but the selected one (:1142-1144)
+        float d_o = INFINITY;
+        for (int k = 0; k < K1; ++k)
+            if (k != sel) d_o = fminf(d_o, nl[k] - mn);
+        float s_den = 0.f;
+        for (int k = 0; k < K1; ++k) {
+            const float dk = nl[k] - mn;
+            if (k != sel && dk <= F64_UNDERFLOW) s_den += expf(-(dk - d_o));
+        }
+        const float log_den = (s_den > 0.f) ? logf(s_den) - d_o : -INFINITY;
+        float log_rg = log_num - log_den;
+        if (!isfinite(log_rg)) log_rg = 1e-15f;                                        // :1156-1159
+        const float ua = uacc_inject ? uacc_inject[n] : bt_uniform(seed, t, BT_PURPOSE_MTM_UACC, site, g);
+        const bool acc = logf(ua) < log_rg;
+        accept[n] = acc ? 1.f : 0.f;
+        logpa[n] = log_rg;
+        if (acc) {
+            accepted_any[n] = 1;
+            const size_t row = (size_t)i * K1 + sel;
+            for (int d = 0; d < D; ++d) {
+                theta[(size_t)n * D + d] = cand_rows[row * D + d];                 // :1164-1168
+                jt[(size_t)n * D + d] = 0;                                         // :1174-1178
+            }
+        }
+    }
+}
+
+// end of the MTM iteration (my_sampler.py:1182-1197): likelihood refresh + v update on accepted pixels
+__global__ void mtm_finish_kernel(PriorDev pr, FmapDev fm, int N, int D, int L, int max_degree,
+                                  const float* __restrict__ theta, const int* __restrict__ nbr,
+                                  const ObsConst* __restrict__ obs, const float* __restrict__ lf_rows,
+                                  const float* __restrict__ jac_rows, float* __restrict__ nll_lik,
+                                  float* __restrict__ grad_lik, float* __restrict__ lf_cache, float* __restrict__ v,
+                                  float alpha, uint8_t* __restrict__ accepted_any) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float gl[BT_MAX_D];
+    const float nll = lik_row<true>(fm, L, lf_rows + (size_t)n * L, jac_rows + (size_t)n * fm.T * L, obs + (size_t)n * L, gl);
+    nll_lik[n] = nll;
+    for (int l = 0; l < L; ++l) lf_cache[(size_t)n * L + l] = lf_rows[(size_t)n * L + l];
+    float x[BT_MAX_D], gp[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? theta[(size_t)n * D + d] : 0.f;
+    const bool upd = accepted_any[n] != 0;
+    if (upd) prior_eval(pr, theta, nbr + (size_t)n * max_degree, max_degree, D, x, gp);
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) {
+            grad_lik[(size_t)n * D + d] = gl[d];
+            if (upd) {
+                const float g = nan_to_num(gl[d] + gp[d]);
+                v[(size_t)n * D + d] = alpha * v[(size_t)n * D + d] + (1.0f - alpha) * g * g;   // :1189-1195
+            }
+        }
+    accepted_any[n] = 0;
+}
+
+// ---- reductions -----------------------------------------------------------------------------
+// out[0] = sum nll, out[1..D] spatial per dim (global convention, factor 1/2), out[1+D..2D] indicator per dim
+__global__ void objective_terms_kernel(PriorDev pr, int N, int D, int max_degree, const float* __restrict__ theta,
+                                       const int* __restrict__ nbr, const float* __restrict__ nll_lik,
+                                       const uint8_t* __restrict__ owned, double* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    double part[1 + 2 * BT_MAX_D];
+#pragma unroll
+    for (int q = 0; q < 1 + 2 * BT_MAX_D; ++q) part[q] = 0.0;
+    if (n < N && (!owned || owned[n])) {
+        float x[BT_MAX_D], had[BT_MAX_D], lap[BT_MAX_D];
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? theta[(size_t)n * D + d] : 0.f;
+        part[0] = nll_lik[n];
+        if (pr.has_spatial) {
+            neighbour_sums(theta, nbr + (size_t)n * max_degree, max_degree, D, x, had, lap);
+#pragma unroll
+            for (int d = 0; d < BT_MAX_D; ++d)
+                if (d < D) part[1 + d] = 0.5 * (double)pr.tau[d] * (double)had[d];
+        }
+        if (pr.has_indicator) {
+#pragma unroll
+            for (int d = 0; d < BT_MAX_D; ++d)
+                if (d < D) {
+                    float dist = 0.f;
+                    if (x[d] > pr.hi[d]) dist = x[d] - pr.hi[d];
+                    else if (x[d] < pr.lo[d]) dist = pr.lo[d] - x[d];
+                    const double sc = (double)dist * (double)pr.inv_delta;
+                    part[1 + D + d] = sc * sc * sc * sc;
+                }
+        }
+    }
+    for (int q = 0; q < 1 + 2 * D; ++q) {
+        double val = part[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if ((threadIdx.x & 31) == 0 && val != 0.0) atomicAdd(out + q, val);
+    }
+}
+
+__global__ void reduce_stats_kernel(int N, const float* __restrict__ accept, const float* __restrict__ logpa,
+                                    const uint8_t* __restrict__ owned, double* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (n < N && (!owned || owned[n])) { a = accept[n]; b = logpa[n]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ theta, const int* __restrict__ pix, int n, int D, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * D) out[i] = theta[(size_t)pix[i / D] * D + (i % D)];
+}
+__global__ void scatter_rows_kernel(float* __restrict__ theta, const int* __restrict__ pix, int n, int D, const float* __restrict__ in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * D) theta[(size_t)pix[i / D] * D + (i % D)] = in[i];
+}
+
+// debug: the Philox draws the non-injected path would use
+__global__ void debug_pmala_noise_kernel(int n_pix, const int* site_pix, int D, uint64_t seed, int64_t t, int site,
+                                         const int64_t* gid, float* z_out, float* u_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const int n = site_pix[i];
+    const int64_t g = gid ? gid[n] : (int64_t)n;
+    float z[BT_MAX_D];
+    bt_normals(z, D, seed, t, BT_PURPOSE_PMALA_Z, site, g, 0u);
+    for (int d = 0; d < D; ++d) z_out[(size_t)n * D + d] = z[d];
+    u_out[n] = bt_uniform(seed, t, BT_PURPOSE_PMALA_U, site, g);
+}
+__global__ void debug_mtm_u_kernel(int n_pix, const int* site_pix, uint64_t seed, int64_t t, int site, const int64_t* gid,
+                                   float* usel, float* uacc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const int n = site_pix[i];
+    const int64_t g = gid ? gid[n] : (int64_t)n;
+    usel[n] = bt_uniform(seed, t, BT_PURPOSE_MTM_USEL, site, g);
+    uacc[n] = bt_uniform(seed, t, BT_PURPOSE_MTM_UACC, site, g);
+}
+__global__ void debug_scatter_cand_kernel(int n_pix, const int* site_pix, int D, int K, const float* cand_rows, float* cand_full) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_pix * K * D) return;
+    const int d = (int)(idx % D);
+    const long long ik = idx / D;
+    const int k = (int)(ik % K), i = (int)(ik / K);
+    cand_full[((size_t)site_pix[i] * K + k) * D + d] = cand_rows[((size_t)i * (K + 1) + k) * D + d];
+}

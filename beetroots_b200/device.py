@@ -1,0 +1,294 @@
+"""DevicePosterior: the reference ``Posterior`` resident on one B200, behind the C ABI.
+
+Reads everything it needs *from the reference objects by attribute name* (SURVEY.md §7 step 2):
+``posterior.likelihood.{y, sigma_a, sigma_m, omega, log_fm1, log_fp1, forward_map}``,
+``posterior.prior_spatial.{weights, initial_weights, list_edges, dict_sites,
+use_next_nearest_neighbors}``, ``posterior.prior_indicator.{lower_bounds, upper_bounds,
+indicator_margin_scale}``, ``forward_map.{network, arr_fixed_values, list_indices_to_sample}``
+and uploads them once.  ``Posterior`` has ``__slots__`` (modelling/posterior.py:7-15), so the
+device handle lives here and not on the reference object.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib as L
+from .modelling import build_neighbor_table
+from .network import DenseMLPWeights
+
+MLP_FP32 = 0
+MLP_BF16_TC = 1
+
+
+def _network_weights(network) -> DenseMLPWeights:
+    """Accept our container or an nnbma-like torch module (PolynomialNetwork -> DenselyConnected)."""
+    if isinstance(network, DenseMLPWeights):
+        return network
+    if hasattr(network, "to_dense_mlp_weights"):
+        return network.to_dense_mlp_weights()
+    # best-effort extraction from an nnbma PolynomialNetwork: poly.{means,stds}, subnetwork.layers.N[.0].{weight,bias},
+    # subnetwork.output_layer.{weight,bias} (key names of data/models/*/parameters.pth / state_dict.pth)
+    from .network import poly_exponents
+    sd = {k: v.detach().cpu().double().numpy() for k, v in network.state_dict().items()}
+    means = sd["poly.means"]
+    stds = sd["poly.stds"]
+    order = int(getattr(network, "order", 3))
+    n_in = int(network.input_features)
+    ws, bs, i = [], [], 0
+    while True:
+        for key in (f"subnetwork.layers.{i}.weight", f"subnetwork.layers.{i}.0.weight"):
+            if key in sd:
+                ws.append(sd[key])
+                bs.append(sd[key.replace("weight", "bias")])
+                break
+        else:
+            break
+        i += 1
+    w_out, b_out = sd["subnetwork.output_layer.weight"], sd["subnetwork.output_layer.bias"]
+    sub = getattr(getattr(network, "subnetwork", network), "current_output_subset_indices", None)
+    if sub is not None:
+        w_out, b_out = w_out[list(sub)], b_out[list(sub)]
+    net = DenseMLPWeights(n_in, order, poly_exponents(n_in, order), means, stds, ws, bs, w_out, b_out)
+    net.validate()
+    return net
+
+
+class DevicePosterior:
+    def __init__(self, ctx, N, D, L, n_sites, site_keys, site_pixels, max_degree):
+        self._ctx = ctx
+        self.N, self.D, self.L = N, D, L
+        self.n_sites = n_sites
+        self.site_keys = site_keys
+        self.site_pixels = site_pixels      # list of np arrays (local pixel ids)
+        self.max_degree = max_degree
+        self._lib = L.load()
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_posterior(cls, posterior, device: int = 0, global_id: Optional[np.ndarray] = None,
+                       dict_sites: Optional[Dict[int, np.ndarray]] = None, mlp_mode: int = MLP_FP32,
+                       stream: int = 0) -> "DevicePosterior":
+        lib = L.load()
+        lik = posterior.likelihood
+        fm = lik.forward_map
+        N, D, Lines = int(posterior.N), int(posterior.D), int(posterior.L)
+        ps, pi = posterior.prior_spatial, posterior.prior_indicator
+        if ps is not None:
+            nnn = bool(getattr(ps, "use_next_nearest_neighbors", True))
+            max_degree = 8 if nnn else 4
+            nbr = build_neighbor_table(ps.list_edges, N, max_degree)
+        else:
+            max_degree, nbr = 1, -np.ones((N, 1), dtype=np.int32)
+        ctx = C.c_void_p()
+        L.check(lib.bt_ctx_create(C.byref(ctx), device, N, D, Lines, max_degree), "bt_ctx_create")
+        self = cls(ctx, N, D, Lines, 0, [], [], max_degree)
+        try:
+            if stream:
+                L.check(lib.bt_set_stream(ctx, stream), "bt_set_stream")
+            net = _network_weights(fm.network)
+            assert net.n_out == Lines, "restrict the network to the fitted lines first"
+            nb = len(net.weights)
+            Ws = [L.as_f64(w) for w in net.weights]
+            Bs = [L.as_f64(b) for b in net.biases]
+            WP = (L.c_double_p * max(nb, 1))(*[L.dptr(w) for w in Ws])
+            BP = (L.c_double_p * max(nb, 1))(*[L.dptr(b) for b in Bs])
+            exps = L.as_i32(net.exponents)
+            means, stds = L.as_f64(net.poly_means), L.as_f64(net.poly_stds)
+            bnew = L.as_i32(np.array(net.block_new, dtype=np.int32))
+            w_out, b_out = L.as_f64(net.w_out), L.as_f64(net.b_out)
+            L.check(lib.bt_upload_network(ctx, net.n_in, net.order, net.n_feat0, L.dptr(exps, C.c_int32), L.dptr(means),
+                                          L.dptr(stds), nb, L.dptr(bnew, C.c_int32), WP, BP, L.dptr(w_out),
+                                          L.dptr(b_out), net.n_out), "bt_upload_network")
+            fixed = L.as_f64(fm.arr_fixed_values)
+            idx = L.as_i32(np.array(fm.list_indices_to_sample, dtype=np.int32))
+            L.check(lib.bt_upload_forward_map(ctx, fixed.size, L.dptr(fixed), idx.size, L.dptr(idx, C.c_int32)),
+                    "bt_upload_forward_map")
+            arrs = [L.as_f64(np.broadcast_to(np.asarray(getattr(lik, k), dtype=np.float64), (N, Lines)))
+                    for k in ("y", "sigma_a", "sigma_m", "omega", "log_fm1", "log_fp1")]
+            L.check(lib.bt_upload_observations(ctx, *[L.dptr(a) for a in arrs]), "bt_upload_observations")
+            self._upload_priors(ps, pi)
+            sites = dict_sites if dict_sites is not None else posterior.dict_sites
+            self.site_keys = list(sites.keys())
+            self.site_pixels = [L.as_i32(np.asarray(sites[k])) for k in self.site_keys]
+            self.n_sites = len(self.site_keys)
+            sizes = L.as_i32(np.array([p.size for p in self.site_pixels], dtype=np.int32))
+            pix = L.as_i32(np.concatenate(self.site_pixels)) if self.n_sites else np.zeros(0, np.int32)
+            gid = None if global_id is None else np.ascontiguousarray(global_id, dtype=np.int64)
+            L.check(lib.bt_upload_graph(ctx, L.dptr(L.as_i32(nbr), C.c_int32), self.n_sites, L.dptr(sizes, C.c_int32),
+                                        L.dptr(pix, C.c_int32), L.dptr(gid, C.c_int64)), "bt_upload_graph")
+            if mlp_mode != MLP_FP32:
+                L.check(lib.bt_set_mlp_mode(ctx, mlp_mode), "bt_set_mlp_mode")
+        except Exception:
+            lib.bt_ctx_destroy(ctx)
+            self._ctx = None
+            raise
+        return self
+
+    def _upload_priors(self, ps, pi):
+        D = self.D
+        tau = L.as_f64(ps.weights) if ps is not None else np.zeros(D)
+        tau0 = L.as_f64(ps.initial_weights) if ps is not None else np.zeros(D)
+        lo = L.as_f64(pi.lower_bounds) if pi is not None else np.zeros(D)
+        hi = L.as_f64(pi.upper_bounds) if pi is not None else np.zeros(D)
+        delta = float(pi.indicator_margin_scale) if pi is not None else 1.0
+        L.check(self._lib.bt_upload_priors(self._ctx, int(ps is not None), L.dptr(tau), L.dptr(tau0), int(pi is not None),
+                                           L.dptr(lo), L.dptr(hi), delta), "bt_upload_priors")
+
+    def update_spatial_weights(self, ps, pi):
+        """posterior.prior_spatial.weights changed (sampler/my_sampler.py:415)."""
+        self._upload_priors(ps, pi)
+
+    def close(self):
+        if self._ctx is not None:
+            self._lib.bt_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state
+    def set_mlp_mode(self, mode: int):
+        L.check(self._lib.bt_set_mlp_mode(self._ctx, mode), "bt_set_mlp_mode")
+
+    def set_state(self, Theta=None, v=None, j=None):
+        Theta, v, j = L.as_f64(Theta), L.as_f64(v), L.as_i32(j)
+        for a in (Theta, v, j):
+            assert a is None or a.size == self.N * self.D
+        L.check(self._lib.bt_set_state(self._ctx, L.dptr(Theta), L.dptr(v), L.dptr(j, C.c_int32)), "bt_set_state")
+
+    def get_state(self, want_v=True, want_j=True):
+        Theta = np.empty((self.N, self.D))
+        v = np.empty((self.N, self.D)) if want_v else None
+        j = np.empty((self.N, self.D), dtype=np.int32) if want_j else None
+        L.check(self._lib.bt_get_state(self._ctx, L.dptr(Theta), L.dptr(v), L.dptr(j, C.c_int32)), "bt_get_state")
+        return Theta, v, j
+
+    def compute_all(self, Theta=None) -> dict:
+        """Posterior.compute_all (modelling/posterior.py:332-446), evaluated on the GPU."""
+        if Theta is not None:
+            assert np.sum(np.isnan(Theta)) == 0, np.sum(np.isnan(Theta))    # posterior.py:360
+            self.set_state(Theta)
+        L.check(self._lib.bt_compute_all(self._ctx), "bt_compute_all")
+        return self.get_current()
+
+    def refresh(self):
+        L.check(self._lib.bt_compute_all(self._ctx), "bt_compute_all")
+
+    def init_v_from_grad(self):
+        L.check(self._lib.bt_init_v_from_grad(self._ctx), "bt_init_v_from_grad")
+
+    def get_current(self, with_forward_map=True) -> dict:
+        N, D, Ln = self.N, self.D, self.L
+        log_f = np.empty((N, Ln)) if with_forward_map else None
+        nll = np.empty(N)
+        gl = np.empty((N, D))
+        oc, og, g = np.empty(N), np.empty(N), np.empty((N, D))
+        L.check(self._lib.bt_get_current(self._ctx, L.dptr(log_f), L.dptr(nll), L.dptr(gl), L.dptr(oc), L.dptr(og),
+                                         L.dptr(g)), "bt_get_current")
+        Theta, _, _ = self.get_state(False, False)
+        fm = {"log_f_Theta": log_f, "f_Theta": np.exp(log_f)} if with_forward_map else {}
+        return {
+            "Theta": Theta, "forward_map_evals": fm,
+            "nll_utils": {"nll": np.float64(nll.sum())},
+            "nll_pix": nll, "grad_lik": gl,
+            "objective_pix_chromatic": oc, "objective_pix_global": og,
+            "objective_chromatic": float(oc.sum()), "objective_global": float(og.sum()), "grad": g,
+        }
+
+    def objective_terms(self, owned=None) -> dict:
+        """dict_objective of Posterior.compute_all_for_saver (posterior.py:270-330)."""
+        out = np.zeros(2 + 2 * self.D)
+        ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+        L.check(self._lib.bt_objective_terms(self._ctx, L.dptr(ow, C.c_uint8), L.dptr(out)), "bt_objective_terms")
+        D = self.D
+        return {"nll": np.float64(out[0]), "nl_prior_spatial": out[1:1 + D].copy(),
+                "nl_prior_indicator": out[1 + D:1 + 2 * D].copy(), "objective": float(out[1 + 2 * D])}
+
+    def forward_map(self, Theta: np.ndarray, compute_derivatives: bool = False) -> dict:
+        """ForwardMap.compute_all on arbitrary rows (neural_network_approx.py:152-305)."""
+        Theta = L.as_f64(Theta)
+        M = Theta.shape[0]
+        lf = np.empty((M, self.L))
+        glf = np.empty((M, self.D, self.L)) if compute_derivatives else None
+        L.check(self._lib.bt_forward_map(self._ctx, M, L.dptr(Theta), L.dptr(lf), L.dptr(glf)), "bt_forward_map")
+        out = {"log_f_Theta": lf, "f_Theta": np.exp(lf)}
+        if compute_derivatives:
+            out["grad_log_f_Theta"] = glf
+            out["grad_f_Theta"] = glf * out["f_Theta"][:, None, :]
+        return out
+
+    # ------------------------------------------------------------------ kernels
+    def begin_iteration(self):
+        L.check(self._lib.bt_begin_iteration(self._ctx), "bt_begin_iteration")
+
+    def pmala_site(self, site, eps, eta, alpha, seed, t, z=None, u=None):
+        z, u = L.as_f32(z), L.as_f32(u)
+        L.check(self._lib.bt_pmala_site(self._ctx, site, eps, eta, alpha, seed, t, L.dptr(z, C.c_float),
+                                        L.dptr(u, C.c_float)), "bt_pmala_site")
+
+    def mtm_site(self, site, K, seed, t, cand=None, u_sel=None, u_acc=None):
+        cand, u_sel, u_acc = L.as_f32(cand), L.as_f32(u_sel), L.as_f32(u_acc)
+        L.check(self._lib.bt_mtm_site(self._ctx, site, K, seed, t, L.dptr(cand, C.c_float), L.dptr(u_sel, C.c_float),
+                                      L.dptr(u_acc, C.c_float)), "bt_mtm_site")
+
+    def mtm_finish(self, alpha):
+        L.check(self._lib.bt_mtm_finish(self._ctx, alpha), "bt_mtm_finish")
+
+    def step_stats(self):
+        a, lp = np.empty(self.N), np.empty(self.N)
+        L.check(self._lib.bt_get_step_stats(self._ctx, L.dptr(a), L.dptr(lp)), "bt_get_step_stats")
+        return a, lp
+
+    def reduce_step_stats(self, owned=None):
+        out = np.zeros(2)
+        ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+        L.check(self._lib.bt_reduce_step_stats(self._ctx, L.dptr(ow, C.c_uint8), L.dptr(out)), "bt_reduce_step_stats")
+        return out
+
+    def debug_philox_pmala(self, site, seed, t):
+        z = np.zeros((self.N, self.D), dtype=np.float32)
+        u = np.zeros(self.N, dtype=np.float32)
+        L.check(self._lib.bt_debug_philox_pmala(self._ctx, site, seed, t, L.dptr(z, C.c_float), L.dptr(u, C.c_float)),
+                "bt_debug_philox_pmala")
+        return z, u
+
+    def debug_philox_mtm(self, site, K, seed, t):
+        cand = np.zeros((self.N, K, self.D), dtype=np.float32)
+        us = np.zeros(self.N, dtype=np.float32)
+        ua = np.zeros(self.N, dtype=np.float32)
+        L.check(self._lib.bt_debug_philox_mtm(self._ctx, site, K, seed, t, L.dptr(cand, C.c_float), L.dptr(us, C.c_float),
+                                              L.dptr(ua, C.c_float)), "bt_debug_philox_mtm")
+        return cand, us, ua
+
+    def synchronize(self):
+        L.check(self._lib.bt_synchronize(self._ctx), "bt_synchronize")
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.bt_kernel_launches(self._ctx))
+
+    def mlp_profile(self, enable=True, reset=False):
+        ms, rows, launches = C.c_double(), C.c_int64(), C.c_int64()
+        L.check(self._lib.bt_mlp_profile(self._ctx, int(enable), int(reset), C.byref(ms), C.byref(rows),
+                                         C.byref(launches)), "bt_mlp_profile")
+        return ms.value, rows.value, launches.value
+
+    # raw pointer plumbing for halo exchange / e2e bench (device or pinned-host addresses as ints)
+    def set_theta_f32_ptr(self, host_ptr: int):
+        L.check(self._lib.bt_set_theta_f32(self._ctx, C.c_void_p(host_ptr)), "bt_set_theta_f32")
+
+    def get_theta_f32_ptr(self, host_ptr: int):
+        L.check(self._lib.bt_get_theta_f32(self._ctx, C.c_void_p(host_ptr)), "bt_get_theta_f32")
+
+    def gather_theta_rows(self, pix_dev_ptr: int, n: int, out_dev_ptr: int):
+        L.check(self._lib.bt_gather_theta_rows(self._ctx, C.c_void_p(pix_dev_ptr), n, C.c_void_p(out_dev_ptr)),
+                "bt_gather_theta_rows")
+
+    def scatter_theta_rows(self, pix_dev_ptr: int, n: int, in_dev_ptr: int):
+        L.check(self._lib.bt_scatter_theta_rows(self._ctx, C.c_void_p(pix_dev_ptr), n, C.c_void_p(in_dev_ptr)),
+                "bt_scatter_theta_rows")

@@ -1,0 +1,222 @@
+"""B200Sampler: drop-in for the reference ``MySampler`` (sampler/my_sampler.py:19-1202).
+
+Same constructor, same ``sample(...)`` signature and Saver protocol; the two transition kernels
+(``generate_new_sample_mtm``, ``generate_new_sample_pmala_rmsprop``) run on the GPU through the
+C ABI.  CUDA state is created lazily inside ``sample`` so the object survives the
+``copy.deepcopy(sampler_)`` of RunMCMC (inversion/run/run_mcmc.py:164-167); do not use it from a
+forked worker (can_run_in_parallel must be False, as the reference already requires for GPU
+forward maps, simulations/astro/toy_case/toy_case_nn.py:162,172).
+
+Noise: the kernel type is drawn from ``self.rng`` exactly like the reference (:430-435); all
+per-pixel draws come from a counter-based Philox stream keyed on (seed, t, site, global pixel
+id), with the 64-bit seed drawn once from ``self.rng`` -- so a chain is reproducible from
+``rng`` and independent of how the map is sharded over GPUs.
+"""
+from __future__ import annotations
+
+from sys import byteorder
+from typing import List, Optional, Union
+
+import numpy as np
+
+from .device import MLP_FP32, DevicePosterior
+
+
+class MySamplerParams:
+    """Mirror of sampler/utils/my_sampler_params.py:9-74 (same asserts)."""
+
+    __slots__ = ("initial_step_size", "extreme_grad", "history_weight", "selection_probas", "k_mtm",
+                 "is_stochastic", "compute_correction_term")
+
+    def __init__(self, initial_step_size: float, extreme_grad: float, history_weight: float,
+                 selection_probas: Union[np.ndarray, List[float]], k_mtm: int, is_stochastic: bool = True,
+                 compute_correction_term: bool = True) -> None:
+        assert initial_step_size > 0
+        assert extreme_grad > 0
+        assert 0 < history_weight < 1
+        assert isinstance(k_mtm, int) and k_mtm >= 1
+        if isinstance(selection_probas, list):
+            selection_probas = np.array(selection_probas)
+        assert np.all(0 <= selection_probas)
+        assert selection_probas.sum() == 1
+        assert isinstance(is_stochastic, bool)
+        assert isinstance(compute_correction_term, bool)
+        self.initial_step_size = initial_step_size
+        self.extreme_grad = extreme_grad
+        self.history_weight = history_weight
+        self.selection_probas = selection_probas
+        self.k_mtm = k_mtm
+        self.is_stochastic = is_stochastic
+        self.compute_correction_term = compute_correction_term
+
+
+class B200Sampler:
+    def __init__(self, my_sampler_params, D: int, L: int, N: int,
+                 rng: np.random.Generator = None, device: int = 0, mlp_mode: int = MLP_FP32):
+        p = my_sampler_params
+        self.eps0 = p.initial_step_size
+        self.lambda_ = p.extreme_grad
+        self.alpha = p.history_weight
+        self.k_mtm = p.k_mtm
+        self.selection_probas = np.asarray(p.selection_probas, dtype=np.float64)
+        assert np.sum(self.selection_probas) == 1, f"{self.selection_probas} should sum to 1"
+        self.stochastic = p.is_stochastic
+        self.compute_correction_term = p.compute_correction_term
+        if not self.stochastic:
+            raise NotImplementedError("optimisation mode (is_stochastic=False) is not on the GPU path yet "
+                                      "(SURVEY.md §8f rank 4)")
+        if self.compute_correction_term:
+            raise NotImplementedError("the PMALA correction term needs the Hessian diagonal, which the reference "
+                                      "itself cannot evaluate with a spatial prior (posterior.py:259); "
+                                      "use compute_correction_term=False")
+        self.D, self.L, self.N = D, L, N
+        self.rng = np.random.default_rng(42) if rng is None else rng
+        self.device = device
+        self.mlp_mode = mlp_mode
+        self.v = np.zeros((N * D,))
+        self.j_t = np.zeros((N * D,))
+        self.current = {}
+        self.philox_seed = None
+        self._dev: Optional[DevicePosterior] = None
+        self._dev_owner = None
+
+    # ------------------------------------------------------------------ reference API
+    def get_rng_state(self):
+        """sampler/abstract_sampler.py:48-73 (numpy>=2-safe)."""
+        st = self.rng.bit_generator.state["state"]
+        return (np.array(bytearray(st["state"].to_bytes(32, byteorder))),
+                np.array(bytearray(st["inc"].to_bytes(32, byteorder))))
+
+    def set_rng_state(self, state_bytes, inc_bytes):
+        """sampler/abstract_sampler.py:75-93."""
+        state = self.rng.bit_generator.state
+        state["state"]["state"] = int.from_bytes(state_bytes, byteorder)
+        state["state"]["inc"] = int.from_bytes(inc_bytes, byteorder)
+        self.rng.bit_generator.state = state
+
+    def generate_random_start_Theta(self, posterior):
+        """sampler/abstract_sampler.py:95-121."""
+        if posterior.prior_indicator is not None:
+            lo, hi = posterior.prior_indicator.lower_bounds, posterior.prior_indicator.upper_bounds
+            return self.rng.uniform(0, 1, size=(posterior.N, posterior.D)) * (hi - lo)[None, :] + lo[None, :]
+        return self.rng.standard_normal(size=(posterior.N, posterior.D))
+
+    def generate_random_start_Theta_1pix(self, Theta, posterior, idx_pix):
+        """The MTM proposals are drawn inside the MTM kernel on the device
+        (sampler/my_sampler.py:103-156 -> csrc/sampler_kernels.cuh mtm_gen_kernel)."""
+        raise NotImplementedError("proposals are generated on the device; see DevicePosterior.debug_philox_mtm")
+
+    # ------------------------------------------------------------------ device plumbing
+    def attach(self, posterior, dev: Optional[DevicePosterior] = None):
+        if dev is not None:
+            self._dev, self._dev_owner = dev, None
+        elif self._dev is None or self._dev_owner is not posterior:
+            self._dev = DevicePosterior.from_posterior(posterior, device=self.device, mlp_mode=self.mlp_mode)
+            self._dev_owner = posterior
+        return self._dev
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, val in self.__dict__.items():
+            setattr(new, k, None if k in ("_dev", "_dev_owner") else copy.deepcopy(val, memo))
+        return new
+
+    def _pull_state(self, with_current=True):
+        dev = self._dev
+        Theta, v, j = dev.get_state()
+        self.v = v.reshape(-1)
+        self.j_t = j.reshape(-1).astype(np.float64)
+        if with_current:
+            self.current = dev.get_current()
+        else:
+            self.current = {"Theta": Theta}
+
+    # ------------------------------------------------------------------ kernels
+    def generate_new_sample_pmala_rmsprop(self, t: int, posterior, noise: Optional[dict] = None):
+        """sampler/my_sampler.py:718-906.  ``noise[s] = {"z": (N, D), "u": (N,)}`` injects the draws."""
+        dev = self.attach(posterior)
+        dev.begin_iteration()
+        for s in range(dev.n_sites):
+            nz = noise[dev.site_keys[s]] if noise is not None else {}
+            dev.pmala_site(s, self.eps0, self.lambda_, self.alpha, self.philox_seed or 0, t, nz.get("z"), nz.get("u"))
+        acc, lpa = dev.reduce_step_stats()
+        return acc / self.N, lpa / self.N
+
+    def generate_new_sample_mtm(self, t: int, posterior, noise: Optional[dict] = None):
+        """sampler/my_sampler.py:966-1202.  ``noise[s] = {"cand": (N, K, D), "u_sel": (N,), "u_acc": (N,)}``."""
+        dev = self.attach(posterior)
+        dev.begin_iteration()
+        for s in range(dev.n_sites):
+            nz = noise[dev.site_keys[s]] if noise is not None else {}
+            dev.mtm_site(s, self.k_mtm, self.philox_seed or 0, t, nz.get("cand"), nz.get("u_sel"), nz.get("u_acc"))
+        dev.mtm_finish(self.alpha)
+        acc, lpa = dev.reduce_step_stats()
+        return acc / self.N, lpa / self.N
+
+    # ------------------------------------------------------------------ main loop
+    def sample(self, posterior, saver, max_iter: int, Theta_0: Optional[np.ndarray] = None,
+               disable_progress_bar: bool = False, regu_spatial_N0: Union[int, float] = np.inf,
+               regu_spatial_scale: float = 1.0, regu_spatial_vmin: float = 1e-8, regu_spatial_vmax: float = 1e8,
+               T_BI: int = 0) -> None:
+        """sampler/my_sampler.py:269-559."""
+        if regu_spatial_N0 < np.inf:
+            raise NotImplementedError("regularisation-weight optimisation is not on the GPU path yet (SURVEY.md §8f rank 3)")
+        additional_sampling_log = {}
+        if Theta_0 is None:
+            print("starting from a random point")
+            Theta_0 = self.generate_random_start_Theta(posterior)
+        assert Theta_0 is not None
+        assert Theta_0.shape == (self.N, self.D)
+        dev = self.attach(posterior)
+        if self.philox_seed is None:
+            self.philox_seed = int(self.rng.integers(0, 2 ** 63 - 1))
+        self.current = dev.compute_all(Theta_0)                                    # :319-323
+        assert np.isnan(self.current["objective_global"]) == 0                    # :325-326
+        assert np.sum(np.isnan(self.current["grad"])) == 0
+        dev.init_v_from_grad()                                                     # :337, :354
+        self.v = self.current["grad"].flatten() ** 2
+        assert np.sum(np.isnan(self.v)) == 0.0
+        assert np.sum(np.isinf(self.v)) == 0.0
+        self.j_t = np.zeros((self.N * self.D,))
+        clppd = np.zeros((self.N, self.L))
+        p_values_y = np.zeros((self.N, self.L))
+        p_values_llh = np.zeros((self.N,))
+
+        try:
+            from tqdm.auto import tqdm
+            it = tqdm(range(1, max_iter + 1), disable=disable_progress_bar)
+        except Exception:                                                          # pragma: no cover
+            it = range(1, max_iter + 1)
+        for t in it:
+            type_t = int(np.argmax(self.rng.multinomial(1, pvals=self.selection_probas)))   # :430-435
+            if type_t == 0:
+                accepted_t, log_proba_accept_t = self.generate_new_sample_mtm(t, posterior)
+            else:
+                accepted_t, log_proba_accept_t = self.generate_new_sample_pmala_rmsprop(t, posterior)
+
+            need = (saver.memory == {}) or saver.check_need_to_update_memory(t)      # :456, :501
+            if need:
+                first = saver.memory == {}
+                self._pull_state(with_current=True)
+                additional_sampling_log["v"] = self.v.reshape((self.N, self.D)) * 1
+                additional_sampling_log["type_t"] = type_t
+                additional_sampling_log["accepted_t"] = accepted_t
+                additional_sampling_log["log_proba_accept_t"] = log_proba_accept_t
+                dict_objective = dev.objective_terms()                             # posterior.py:270-330
+                kw = dict(Theta=self.current["Theta"], forward_map_evals=self.current["forward_map_evals"],
+                          nll_utils=self.current["nll_utils"], dict_objective=dict_objective,
+                          additional_sampling_log=additional_sampling_log)
+                if first:
+                    saver.initialize_memory(max_iter, t, **kw)                     # :478-486
+                rng_state_array, rng_inc_array = self.get_rng_state()
+                saver.update_memory(t, rng_state_array=rng_state_array, rng_inc_array=rng_inc_array, **kw)
+            if saver.check_need_to_save(t):                                        # :539-541
+                saver.save_to_file()
+        self._pull_state(with_current=True)
+        # online model checking (clppd, Bayesian p-values, :158-267) is the next widening row
+        saver.save_additional(list_arrays=[clppd, p_values_y, p_values_llh],
+                              list_names=["clppd", "p-values-y", "p-values-llh"])   # :551-558
+        return

@@ -1,0 +1,157 @@
+/*
+ * beetroots_b200 -- C ABI of the B200-native sampler step (PMALA + MTM) of beetroots.
+ *
+ * The reference is pure Python, so "the FFI a maintainer would bind" is ctypes
+ * (INTEGRATION.md shows the stub).  Every entry point below replaces a method of the reference
+ * on the per-iteration hot path; the reference interface it stands for is cited as file:line
+ * relative to /root/reference/beetroots/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; "host" pointers are ordinary process memory (double /
+ *     int32, C-contiguous, the dtypes the reference uses), "device" pointers are CUDA device
+ *     addresses on the context's GPU;
+ *   - every function returns 0 on success, a negative code otherwise; bt_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - one context = one GPU = one (band of a) map; all work is enqueued on the context's
+ *     stream (bt_set_stream); functions taking or returning HOST data synchronise that stream
+ *     before returning, functions working on device-resident state do not;
+ *   - no hidden global state besides the per-thread error string.
+ */
+#ifndef BEETROOTS_B200_H
+#define BEETROOTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bt_ctx bt_ctx;
+
+#define BT_MAX_D 5        /* kappa, P, radm, Avmax, angle */
+#define BT_MAX_L 64
+#define BT_MAX_DEGREE 8
+
+/* precision of the forward-map kernel */
+#define BT_MLP_FP32 0      /* CUDA-core fp32: the parity path (rtol 1e-5 vs fp64 reference) */
+#define BT_MLP_BF16_TC 1   /* tcgen05 bf16 operands, fp32 accumulation in TMEM */
+
+const char* bt_last_error(void);
+int bt_version(void);
+
+/* N pixels held by this context (owned + ghost), D sampled parameters, L lines. */
+int bt_ctx_create(bt_ctx** out, int device, int N, int D, int L, int max_degree);
+int bt_ctx_destroy(bt_ctx* ctx);
+/* cudaStream_t as an integer (0 = legacy default stream). */
+int bt_set_stream(bt_ctx* ctx, uint64_t cuda_stream);
+int bt_set_mlp_mode(bt_ctx* ctx, int mode);
+int bt_synchronize(bt_ctx* ctx);
+
+/* ---- model upload (once per run) -------------------------------------------------------- */
+
+/* nnbma PolynomialNetwork -> DenselyConnected weights; replaces NeuralNetwork.load +
+ * restrict_to_output_subset, modelling/forward_maps/neural_network_approx.py:38,87-105.
+ * exponents: (n_feat0, order) int32 (-1 padded); weights[l]: (block_new[l], in_l) row-major
+ * with in_l = n_feat0 + sum_{l'<l} block_new[l'];  w_out: (n_out, n_feat_total). */
+int bt_upload_network(bt_ctx* ctx, int n_in, int order, int n_feat0, const int32_t* exponents,
+                      const double* poly_means, const double* poly_stds, int n_blocks,
+                      const int32_t* block_new, const double* const* weights,
+                      const double* const* biases, const double* w_out, const double* b_out,
+                      int n_out);
+
+/* Fixed / sampled entries of theta; replaces ForwardMap.set_sampled_and_fixed_entries,
+ * modelling/forward_maps/abstract_base.py:44-73.  d_full = n_in + 1 (kappa first). */
+int bt_upload_forward_map(bt_ctx* ctx, int d_full, const double* arr_fixed_values,
+                          int d_sampling, const int32_t* list_indices_to_sample);
+
+/* (N, L) host arrays; replaces the attributes read by MixingModelsLikelihood
+ * (modelling/likelihoods/approx_censored_add_mult.py:122-266). */
+int bt_upload_observations(bt_ctx* ctx, const double* y, const double* sigma_a,
+                           const double* sigma_m, const double* omega, const double* log_fm1,
+                           const double* log_fp1);
+
+/* Spatial prior weights (tau = weights, tau_init = initial_weights) and smooth-indicator box;
+ * modelling/priors/abstract_spatial_prior.py:100-121, smooth_indicator_prior.py:133-166. */
+int bt_upload_priors(bt_ctx* ctx, int has_spatial, const double* tau, const double* tau_init,
+                     int has_indicator, const double* lower, const double* upper, double delta);
+
+/* Pixel graph: neighbour table (N, max_degree) int32, -1 padded, neighbour order = order in
+ * SpatialPrior.list_edges (abstract_spatial_prior.py:13-55); colour classes = dict_sites
+ * (:125-153) as concatenated sorted pixel lists; global_id (N) or NULL (= arange) keys the
+ * counter-based RNG so that chains do not depend on how the map is sharded. */
+int bt_upload_graph(bt_ctx* ctx, const int32_t* nbr, int n_sites, const int32_t* site_sizes,
+                    const int32_t* site_pixels, const int64_t* global_id);
+
+/* ---- state ------------------------------------------------------------------------------ */
+
+/* Theta (N, D) scaled space; v (N, D) RMSProp accumulator; j (N, D) counters.  NULL = keep. */
+int bt_set_state(bt_ctx* ctx, const double* theta, const double* v, const int32_t* j);
+int bt_get_state(bt_ctx* ctx, double* theta, double* v, int32_t* j);
+/* float32 variants for the end-to-end bench / halo plumbing (host pointers). */
+int bt_set_theta_f32(bt_ctx* ctx, const float* theta);
+int bt_get_theta_f32(bt_ctx* ctx, float* theta);
+/* device-side gather / scatter of theta rows (halo exchange buffers live in torch tensors). */
+int bt_gather_theta_rows(bt_ctx* ctx, const int32_t* pix_dev, int n, float* out_dev);
+int bt_scatter_theta_rows(bt_ctx* ctx, const int32_t* pix_dev, int n, const float* in_dev);
+
+/* Posterior.compute_all (modelling/posterior.py:332-446) at the resident Theta: forward map +
+ * Jacobian, likelihood value and gradient, cached per pixel. */
+int bt_compute_all(bt_ctx* ctx);
+/* v <- grad^2, j <- 0  (sampler/my_sampler.py:337,354). */
+int bt_init_v_from_grad(bt_ctx* ctx);
+/* Any pointer may be NULL.  log_f (N, L), nll_pix (N), grad_lik (N, D), obj_chromatic (N),
+ * obj_global (N), grad (N, D): the entries of the ``current`` dict (posterior.py:421-446). */
+int bt_get_current(bt_ctx* ctx, double* log_f, double* nll_pix, double* grad_lik,
+                   double* obj_chromatic, double* obj_global, double* grad);
+/* dict_objective of Posterior.compute_all_for_saver (posterior.py:270-330):
+ * out[0] = nll, out[1..D] = nl_prior_spatial per dim, out[1+D..2D] = nl_prior_indicator per dim,
+ * out[1+2D] = objective.  Sums run over pixels flagged in owned (N uint8) or all if NULL. */
+int bt_objective_terms(bt_ctx* ctx, const uint8_t* owned, double* out);
+
+/* ForwardMap.compute_all on arbitrary rows (neural_network_approx.py:152-305): theta (M, D)
+ * host -> log_f (M, L), grad_log_f (M, D, L) or NULL. */
+int bt_forward_map(bt_ctx* ctx, int M, const double* theta, double* log_f, double* grad_log_f);
+
+/* ---- transition kernels, one colour class (site) at a time -------------------------------- */
+
+/* MySampler.generate_new_sample_pmala_rmsprop, sampling branch, body of the site loop
+ * (sampler/my_sampler.py:752-903).  z_inject (N, D) standard normals / u_inject (N) uniforms
+ * are HOST float arrays indexed by local pixel, or NULL to draw from Philox(seed, t). */
+int bt_pmala_site(bt_ctx* ctx, int site, double eps, double eta, double alpha, uint64_t seed,
+                  int64_t t, const float* z_inject, const float* u_inject);
+
+/* MySampler.generate_new_sample_mtm, sampling branch, body of the site loop
+ * (sampler/my_sampler.py:1006-1178) with proposals of sampler/utils/utils.py:274-349 and the
+ * proposal density of :419-495.  cand_inject (N, K, D), usel_inject (N), uacc_inject (N) host
+ * float arrays or NULL (Philox). */
+int bt_mtm_site(bt_ctx* ctx, int site, int K, uint64_t seed, int64_t t, const float* cand_inject,
+                const float* usel_inject, const float* uacc_inject);
+/* End of generate_new_sample_mtm (:1182-1197): refresh likelihood terms and update v on the
+ * pixels accepted during this iteration.  Call after all sites (and after the halo exchange). */
+int bt_mtm_finish(bt_ctx* ctx, double alpha);
+/* Clear the per-iteration accept / log-ratio maps (start of either kernel, :736-737, :989-990). */
+int bt_begin_iteration(bt_ctx* ctx);
+
+/* accept (N) in {0,1}, log_proba (N): accept_total / log_proba_accept_total (:882-883,
+ * :1170-1171).  Host pointers, may be NULL. */
+int bt_get_step_stats(bt_ctx* ctx, double* accept, double* log_proba);
+/* out[0] = sum accept, out[1] = sum log_proba over pixels flagged in owned (or all). */
+int bt_reduce_step_stats(bt_ctx* ctx, const uint8_t* owned, double* out);
+
+/* Fill out (n) with the standard normals / uniforms the Philox path would use for
+ * (purpose, site, t): lets tests replay the device noise through the oracle. */
+int bt_debug_philox_pmala(bt_ctx* ctx, int site, uint64_t seed, int64_t t, float* z_out,
+                          float* u_out);
+int bt_debug_philox_mtm(bt_ctx* ctx, int site, int K, uint64_t seed, int64_t t, float* cand_out,
+                        float* usel_out, float* uacc_out);
+
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t bt_kernel_launches(bt_ctx* ctx);
+/* device time (ms) spent in the forward-map kernel since the last call with reset != 0 and the
+ * number of rows it processed; measured with CUDA events on the context's stream. */
+int bt_mlp_profile(bt_ctx* ctx, int enable, int reset, double* ms, int64_t* rows, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEETROOTS_B200_H */

@@ -1,0 +1,259 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle and the reference goldens.
+
+Tolerances (float32 kernels vs float64 reference): per-pixel objectives / gradients rtol 1e-5
+relative to the array scale, states rtol 1e-5, accept / reject decisions identical."""
+import numpy as np
+import pytest
+
+from _cases import GOLDEN_CASES, golden_noise, load_golden, problem_from_golden, slice_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def scaled_err(a, b):
+    """max |a-b| / (|b| + scale): float32 rounding is relative to the magnitude of the sums involved."""
+    scale = np.maximum(np.abs(b), np.percentile(np.abs(b), 90) + 1e-12)
+    return np.max(np.abs(a - b) / scale)
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from beetroots_b200 import _lib
+    return _lib.load()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_compute_all_vs_reference_golden(lib, name):
+    from beetroots_b200 import DevicePosterior
+    g = load_golden(name)
+    post, _ = problem_from_golden(g)
+    dev = DevicePosterior.from_posterior(post)
+    cur = dev.compute_all(g["theta0"])
+    assert np.max(np.abs(cur["forward_map_evals"]["log_f_Theta"] - g["init_log_f"])) < 5e-6
+    assert scaled_err(cur["nll_pix"], g["init_nll_pix"]) < 1e-5
+    assert scaled_err(cur["grad_lik"], g["init_grad_lik"]) < 1e-5
+    assert scaled_err(cur["objective_pix_chromatic"], g["init_obj_chrom"]) < 1e-5
+    assert scaled_err(cur["objective_pix_global"], g["init_obj_glob"]) < 1e-5
+    assert scaled_err(cur["grad"], g["init_grad"]) < 1e-5
+    fm = dev.forward_map(g["theta0"], compute_derivatives=True)
+    assert np.max(np.abs(fm["grad_log_f_Theta"] - g["init_grad_log_f"])) < 1e-5 * (1 + np.abs(g["init_grad_log_f"]).max())
+    dev.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_steps_vs_reference_golden(lib, name):
+    """Replay the reference's recorded noise tape: same decisions, same states."""
+    from beetroots_b200 import B200Sampler, DevicePosterior, MySamplerParams
+    g = load_golden(name)
+    post, _ = problem_from_golden(g)
+    K = int(g["K"])
+    dev = DevicePosterior.from_posterior(post)
+    dev.compute_all(g["theta0"])
+    dev.init_v_from_grad()
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N)
+    smp.attach(post, dev)
+    for t, kind in enumerate(g["kernels"], start=1):
+        noise = golden_noise(g, t, int(kind), post, full=True)
+        if kind == 1:
+            smp.generate_new_sample_pmala_rmsprop(t, post, noise)
+        else:
+            smp.generate_new_sample_mtm(t, post, noise)
+        acc, lpa = dev.step_stats()
+        th, v, j = dev.get_state()
+        assert np.array_equal(acc > 0, g[f"t{t}_accept"] > 0), f"{name}: accept decisions differ at t={t}"
+        ref_lpa = g[f"t{t}_logpa"]
+        assert np.max(np.abs(lpa - ref_lpa) / (1 + np.abs(ref_lpa))) < 2e-4
+        assert np.allclose(th, g[f"t{t}_Theta"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(v, g[f"t{t}_v"], rtol=2e-5, atol=1e-8 * np.abs(g[f"t{t}_v"]).max())
+        assert np.array_equal(j, g[f"t{t}_j"].astype(np.int32))
+        cur = dev.get_current()
+        assert scaled_err(cur["grad"], g[f"t{t}_grad"]) < 2e-5
+        assert scaled_err(cur["objective_pix_chromatic"], g[f"t{t}_obj_chrom"]) < 2e-5
+    dev.close()
+
+
+def _synthetic(H, W, K, nnn=False, boost=1.0, L=10):
+    from beetroots_b200.synthetic import make_problem
+    from oracle import posterior as OP
+    return make_problem(H, W, lambda fm, th: OP.forward_map_compute_all(fm, th, False)["log_f_Theta"], L=L, k_mtm=K,
+                        use_next_nearest_neighbors=nnn, censor_boost=boost)
+
+
+@pytest.mark.parametrize("nnn,boost", [(False, 1.0), (True, 5.0)])
+def test_philox_chain_vs_oracle(lib, nnn, boost):
+    """30x30 (config c2 shape) chain on the device's own Philox noise, replayed through the oracle."""
+    from beetroots_b200 import B200Sampler, DevicePosterior, MySamplerParams
+    from beetroots_b200 import modelling as M
+    from oracle.sampler import OracleSampler
+    K, seed = 8, 987654321
+    prob = _synthetic(30, 30, K, nnn, boost)
+    post = prob.posterior
+    dev = DevicePosterior.from_posterior(post)
+    dev.compute_all(prob.theta_init)
+    dev.init_v_from_grad()
+    nbr = M.build_neighbor_table(post.prior_spatial.list_edges, post.N, 8 if nnn else 4)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, K)
+    orc.init(prob.theta_init)
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N)
+    smp.attach(post, dev)
+    smp.philox_seed = seed
+    n_dec = n_diff = 0
+    for t, kind in enumerate([1, 0, 1, 0], start=1):
+        if kind == 1:
+            noise = {}
+            for s, key in enumerate(dev.site_keys):
+                z, u = dev.debug_philox_pmala(s, seed, t)
+                noise[key] = {"z": z, "u": u}
+            smp.generate_new_sample_pmala_rmsprop(t, post)
+            o_acc, o_lpa = orc.pmala_step(slice_noise(noise, post))
+        else:
+            # MTM proposals depend on the state left by the previous site: interleave device and oracle site by site
+            dev.begin_iteration()
+            noise = {}
+            for s, key in enumerate(dev.site_keys):
+                c, us, ua = dev.debug_philox_mtm(s, K, seed, t)
+                noise[key] = {"cand": c, "u_sel": us, "u_acc": ua}
+                dev.mtm_site(s, K, seed, t)
+            dev.mtm_finish(0.99)
+            o_acc, o_lpa = orc.mtm_step(slice_noise(noise, post))
+        acc, lpa = dev.step_stats()
+        n_dec += acc.size
+        n_diff += int(np.sum((acc > 0) != (o_acc > 0)))
+        th, v, _ = dev.get_state()
+        same = (acc > 0) == (o_acc > 0)
+        assert np.allclose(th[same], orc.current["Theta"][same], rtol=1e-5, atol=2e-6)
+        # keep the oracle on the device trajectory if a near-tie flipped (none expected)
+        if n_diff:
+            break
+    assert n_diff == 0, f"{n_diff}/{n_dec} accept decisions differ from the oracle"
+    dev.close()
+
+
+def test_philox_injection_equivalence_and_determinism(lib):
+    """Injecting the Philox draws exported by the library reproduces the Philox chain bit-for-bit."""
+    from beetroots_b200 import DevicePosterior
+    K, seed = 5, 4242
+    prob = _synthetic(12, 10, K)
+    post = prob.posterior
+    outs = []
+    for mode in ("philox", "inject", "philox"):
+        dev = DevicePosterior.from_posterior(post)
+        dev.compute_all(prob.theta_init)
+        dev.init_v_from_grad()
+        dev.begin_iteration()
+        for s in range(dev.n_sites):
+            if mode == "inject":
+                z, u = dev.debug_philox_pmala(s, seed, 1)
+                dev.pmala_site(s, 1e-4, 1e-5, 0.99, 0, 1, z, u)
+            else:
+                dev.pmala_site(s, 1e-4, 1e-5, 0.99, seed, 1)
+        dev.begin_iteration()
+        for s in range(dev.n_sites):
+            if mode == "inject":
+                c, us, ua = dev.debug_philox_mtm(s, K, seed, 2)
+                dev.mtm_site(s, K, 0, 2, c, us, ua)
+            else:
+                dev.mtm_site(s, K, seed, 2)
+        dev.mtm_finish(0.99)
+        outs.append(dev.get_state())
+        dev.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert np.array_equal(a, b)
+
+
+def test_sample_runs_with_saver_protocol(lib):
+    """Full ``sample`` loop against an in-memory saver speaking the reference Saver protocol."""
+    from beetroots_b200 import B200Sampler, MySamplerParams
+
+    class MemSaver:
+        def __init__(self):
+            self.memory, self.saved, self.additional, self.t0 = {}, [], None, None
+
+        def initialize_memory(self, T_MC, t, **kw):
+            self.t0 = t
+            self.memory = {"list_Theta": [], "list_objective": []}
+
+        def update_memory(self, t, Theta, dict_objective, **kw):
+            self.memory["list_Theta"].append(Theta.copy())
+            self.memory["list_objective"].append(dict_objective["objective"])
+            assert set(dict_objective) == {"nll", "nl_prior_spatial", "nl_prior_indicator", "objective"}
+            assert kw["rng_state_array"].shape == (32,)
+
+        def check_need_to_update_memory(self, t):
+            return True
+
+        def check_need_to_save(self, t):
+            return t % 5 == 0
+
+        def save_to_file(self):
+            self.saved.append(self.memory)
+            self.memory = {}
+
+        def save_additional(self, list_arrays, list_names):
+            self.additional = dict(zip(list_names, list_arrays))
+
+    prob = _synthetic(10, 10, 6)
+    post = prob.posterior
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], 6, True, False), post.D, post.L, post.N,
+                      rng=np.random.default_rng(3))
+    sv = MemSaver()
+    smp.sample(post, sv, 10, Theta_0=prob.theta_init, disable_progress_bar=True)
+    assert len(sv.saved) == 2 and sum(len(m["list_Theta"]) for m in sv.saved) == 10
+    objs = np.concatenate([m["list_objective"] for m in sv.saved])
+    assert np.all(np.isfinite(objs))
+    assert set(sv.additional) == {"clppd", "p-values-y", "p-values-llh"}
+    assert smp.current["Theta"].shape == (post.N, post.D) and np.all(np.isfinite(smp.v))
+
+
+def test_full_size_properties(lib):
+    """Size-independent properties at a large map (256x256, K=10): determinism, untouched colours,
+    objective bookkeeping, sane acceptance."""
+    from beetroots_b200 import DevicePosterior
+    from beetroots_b200.synthetic import make_problem
+    H = W = 256
+    holder = {}
+
+    def gpu_forward(fm, theta):
+        from beetroots_b200 import modelling as M
+        N = theta.shape[0]
+        lik = M.MixingModelsLikelihood(fm, 4, fm.L, N, np.ones((N, fm.L)), 1.0, 0.1, 0.5, a0=np.zeros((1, fm.L)),
+                                       a1=np.ones((1, fm.L)))
+        d = DevicePosterior.from_posterior(M.Posterior(4, fm.L, N, lik, None, None))
+        holder["lf"] = d.forward_map(theta)["log_f_Theta"]
+        d.close()
+        return holder["lf"]
+
+    prob = make_problem(H, W, gpu_forward, L=10, k_mtm=10)
+    post = prob.posterior
+    dev = DevicePosterior.from_posterior(post)
+    cur0 = dev.compute_all(prob.theta_init)
+    dev.init_v_from_grad()
+    assert np.all(np.isfinite(cur0["objective_pix_chromatic"])) and np.all(np.isfinite(cur0["grad"]))
+    # idempotence: recomputing at the same Theta gives bit-identical results
+    cur1 = dev.compute_all()
+    assert np.array_equal(cur0["grad"], cur1["grad"])
+    th0, _, _ = dev.get_state()
+    dev.begin_iteration()
+    dev.pmala_site(0, 1e-4, 1e-5, 0.99, 7, 1)
+    th1, _, _ = dev.get_state()
+    other = post.dict_sites[1]
+    assert np.array_equal(th0[other], th1[other]), "a colour sweep must not touch the other colour"
+    acc, _ = dev.step_stats()
+    assert 0.5 < acc[post.dict_sites[0]].mean() <= 1.0
+    dev.begin_iteration()
+    for s in range(dev.n_sites):
+        dev.mtm_site(s, 10, 7, 2)
+    dev.mtm_finish(0.99)
+    acc, lrg = dev.step_stats()
+    assert 0.0 < acc.mean() < 1.0 and np.all(np.isfinite(lrg))
+    # cached likelihood terms equal a fresh compute_all at the final state
+    a = dev.get_current()
+    b = dev.compute_all()
+    assert np.allclose(a["nll_pix"], b["nll_pix"], rtol=1e-6, atol=1e-5)
+    terms = dev.objective_terms()
+    assert np.isclose(terms["objective"], b["objective_global"], rtol=1e-5)
+    dev.close()

@@ -1,0 +1,106 @@
+"""CPU: the oracle port against (1) the golden vectors recorded from the UNMODIFIED reference
+(tests/golden/make_golden.py) and (2) the reference's own known-answer tests for this path."""
+import numpy as np
+import pytest
+
+from _cases import GOLDEN_CASES, golden_noise, load_golden, problem_from_golden
+from oracle import posterior as OP
+from oracle.sampler import OracleSampler
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / (1e-12 + np.maximum(np.abs(a), np.abs(b))))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_compute_all_matches_reference(name):
+    g = load_golden(name)
+    post, nbr = problem_from_golden(g)
+    cur = OP.compute_all(post, g["theta0"], nbr)
+    assert rel(cur["forward_map_evals"]["log_f_Theta"], g["init_log_f"]) < 1e-12
+    assert rel(cur["forward_map_evals"]["grad_log_f_Theta"], g["init_grad_log_f"]) < 1e-10
+    assert rel(cur["nll_pix"], g["init_nll_pix"]) < 1e-10
+    assert rel(cur["grad_lik"], g["init_grad_lik"]) < 1e-9
+    assert rel(cur["objective_pix_chromatic"], g["init_obj_chrom"]) < 1e-10
+    assert rel(cur["objective_pix_global"], g["init_obj_glob"]) < 1e-10
+    assert rel(cur["grad"], g["init_grad"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_steps_match_reference(name):
+    g = load_golden(name)
+    post, nbr = problem_from_golden(g)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, int(g["K"]))
+    orc.init(g["theta0"])
+    for t, kind in enumerate(g["kernels"], start=1):
+        noise = golden_noise(g, t, int(kind), post)
+        acc, lpa = orc.pmala_step(noise) if kind == 1 else orc.mtm_step(noise)
+        assert np.array_equal(acc > 0, g[f"t{t}_accept"] > 0), f"accept decisions differ at t={t}"
+        assert rel(lpa, g[f"t{t}_logpa"]) < 1e-7
+        assert rel(orc.current["Theta"], g[f"t{t}_Theta"]) < 1e-10
+        assert rel(orc.v, g[f"t{t}_v"]) < 1e-8
+        assert np.array_equal(orc.j_t, g[f"t{t}_j"])
+        assert rel(orc.current["grad"], g[f"t{t}_grad"]) < 1e-8
+
+
+# ---- the reference's own known-answer tests for this path, restated on the oracle ------------
+class _Prior:
+    pass
+
+
+def _grid3():
+    from beetroots_b200 import modelling as M
+    X, Y = np.repeat(np.arange(3), 3), np.tile(np.arange(3), 3)
+    sp = M.L22DiscreteGradSpatialPrior(1, 9, X, Y, None, False, np.ones(1))
+    return sp, M.build_neighbor_table(sp.list_edges, 9, 4)
+
+
+def test_l22_known_answers():
+    """/root/reference/tests/modelling/priors/test_l22_discrete_grad_prior.py:61-183."""
+    sp, nbr = _grid3()
+    Theta = np.zeros((9, 1))
+    Theta[4] = 1.0
+    had, lap = OP.spatial_sums(Theta, nbr)
+    assert np.array_equal(lap[:, 0], [0, -1, 0, -1, 4, -1, 0, -1, 0])      # :67-71
+    assert np.array_equal(had[:, 0], [0, 1, 0, 1, 4, 1, 0, 1, 0])          # :92-96
+    chrom = (sp.weights * had).sum()
+    assert chrom == 8 and 0.5 * chrom == 4                                   # :132-135
+    assert np.array_equal(2 * sp.weights * lap, 2 * lap)                     # :168-183
+
+
+def test_indicator_known_answers():
+    """/root/reference/tests/modelling/priors/test_smooth_indicator_prior.py:31-124."""
+    p = _Prior()
+    p.lower_bounds, p.upper_bounds, p.indicator_margin_scale = np.array([-1.0, -1.0]), np.array([1.0, 1.0]), 0.1
+    inside = np.array([[0.0, 0.5]])
+    assert OP.indicator_penalty(inside, p)[0] == 0
+    out = np.array([[1.0 + 0.1 * 10, 0.0]])           # ten margins outside on one side -> (10)^4
+    assert np.isclose(OP.indicator_penalty(out, p)[0], 1e4)                  # :47-48
+    one = np.array([[1.1, -1.1]])                      # one margin outside: grad = +-4/Delta
+    gr = OP.indicator_gradient(one, p)
+    assert np.allclose(gr[0], [4 / 0.1, -4 / 0.1])                           # :87,97
+
+
+def test_mtm_proposal_density_closed_form():
+    """/root/reference/tests/sampler/utils/test_utils.py:51-79: 4 neighbours all at 0, tau = 1:
+    log q(x) = log sum_m C(4,m) m exp(-m^2 x^2)."""
+    from math import comb
+    from beetroots_b200 import modelling as M
+    X, Y = np.repeat(np.arange(3), 3), np.tile(np.arange(3), 3)
+    sp = M.L22DiscreteGradSpatialPrior(1, 9, X, Y, None, False, np.ones(1))
+    nbr = M.build_neighbor_table(sp.list_edges, 9, 4)
+    post = M.Posterior(1, 1, 9, None, sp, None)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, 3)
+    Theta = np.zeros((9, 1))
+    xs = np.array([0.0, 0.3, -1.2, 2.0])
+    val = orc.proposal_log_density(Theta, np.array([4]), xs.reshape(1, 4, 1))[0]
+    expected = np.log(sum(comb(4, m) * m * np.exp(-(m ** 2) * xs ** 2) for m in range(1, 5)))
+    assert np.allclose(val, expected, rtol=1e-12)
+
+
+def test_mills_ratio():
+    """/root/reference/tests/modelling/likelihoods/test_utils.py:6-15."""
+    assert np.isclose(OP._norm_pdf_cdf_ratio(0.0), 2 / np.sqrt(2 * np.pi))
+    x = np.linspace(-30, 10, 200)
+    r = OP._norm_pdf_cdf_ratio(x)
+    assert np.all(np.diff(r) < 0)
