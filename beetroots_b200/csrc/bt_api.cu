@@ -62,6 +62,8 @@ struct bt_ctx {
     // profiling of the forward-map kernel
     bool prof = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> prof_events;   // (start, stop) pairs recorded on the stream, read back lazily
+    size_t prof_used = 0;
     double prof_ms = 0;
     int64_t prof_rows = 0, prof_launches = 0;
 };
@@ -133,6 +135,7 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
                     c->tmpf, c->tmpd, c->owned_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -366,7 +369,15 @@ extern "C" int bt_scatter_theta_rows(bt_ctx* c, const int32_t* pix_dev, int n, c
 // ---- forward map dispatch ----------------------------------------------------------------------
 static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
     if (M <= 0) return 0;
-    if (c->prof) CK(cudaEventRecord(c->ev0, c->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->prof) {
+        if (c->prof_used + 2 > c->prof_events.size()) {
+            for (int q = 0; q < 2; ++q) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->prof_events.push_back(e); }
+        }
+        e0 = c->prof_events[c->prof_used]; e1 = c->prof_events[c->prof_used + 1];
+        c->prof_used += 2;
+        CK(cudaEventRecord(e0, c->stream));
+    }
     if (c->mlp_mode == BT_MLP_BF16_TC) {
         int rc = tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);
         if (rc) return fail("tensor-core MLP launch failed", __FILE__, __LINE__);
@@ -386,17 +397,24 @@ static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
         KLAUNCH(c);
     }
     if (c->prof) {
-        CK(cudaEventRecord(c->ev1, c->stream));
-        CK(cudaEventSynchronize(c->ev1));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        c->prof_ms += ms; c->prof_rows += (int64_t)M * (jac ? 1 + c->fm.T : 1); c->prof_launches++;
+        CK(cudaEventRecord(e1, c->stream));        // no synchronisation here: times are read in bt_mlp_profile
+        c->prof_rows += (int64_t)M * (jac ? 1 + c->fm.T : 1); c->prof_launches++;
     }
     return 0;
 }
 
 extern "C" int bt_mlp_profile(bt_ctx* c, int enable, int reset, double* ms, int64_t* rows, int64_t* launches) {
     REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (c->prof_used) {
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t q = 0; q + 1 < c->prof_used; q += 2) {
+            float t_ms = 0;
+            CK(cudaEventElapsedTime(&t_ms, c->prof_events[q], c->prof_events[q + 1]));
+            c->prof_ms += t_ms;
+        }
+        c->prof_used = 0;
+    }
     if (ms) *ms = c->prof_ms;
     if (rows) *rows = c->prof_rows;
     if (launches) *launches = c->prof_launches;

@@ -292,3 +292,20 @@ class DevicePosterior:
     def scatter_theta_rows(self, pix_dev_ptr: int, n: int, in_dev_ptr: int):
         L.check(self._lib.bt_scatter_theta_rows(self._ctx, C.c_void_p(pix_dev_ptr), n, C.c_void_p(in_dev_ptr)),
                 "bt_scatter_theta_rows")
+
+
+def gpu_log_f(fm, Theta: np.ndarray, device: int = 0, mlp_mode: int = MLP_FP32) -> np.ndarray:
+    """ln f(Theta) of a (mirror or reference) NeuralNetworkApprox evaluated on the GPU, without a Posterior:
+    used to synthesise observations (simulations/astro/observation/abstract_toy_case.py:68-77)."""
+    from .modelling import MixingModelsLikelihood, Posterior
+    Theta = np.ascontiguousarray(Theta, dtype=np.float64)
+    M = Theta.shape[0]
+    Ln = int(fm.L)
+    lik = MixingModelsLikelihood(fm, Theta.shape[1], Ln, M, np.ones((M, Ln)), 1.0, 0.1, 0.5,
+                                 a0=np.zeros((1, Ln)), a1=np.ones((1, Ln)))
+    dev = DevicePosterior.from_posterior(Posterior(Theta.shape[1], Ln, M, lik, None, None), device=device,
+                                         mlp_mode=mlp_mode)
+    try:
+        return dev.forward_map(Theta)["log_f_Theta"]
+    finally:
+        dev.close()

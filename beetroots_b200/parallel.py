@@ -1,0 +1,262 @@
+"""Row-band sharding of the pixel map over the GPUs of one node.
+
+The only cross-pixel dependency of the sampler step is the nearest-neighbour stencil of the
+spatial prior (l22_discrete_grad_prior.py:9-80) and of the MTM proposal (sampler/utils/utils.py
+:100-125), and pixels of one colour class are conditionally independent
+(abstract_spatial_prior.py:125-153).  So rank r owns ``H / G`` consecutive rows (X = slow axis,
+the ``idx`` order of the reference maps), stores one ghost row above and below, and after each
+colour sweep sends its first / last owned row to its neighbours (16 KiB for W=1024, D=4) over
+NCCL.  Likelihood, network and RNG are per pixel: the Philox counters are keyed on the GLOBAL
+pixel id, so the chain is bit-identical for 1, 2, 4 or 8 GPUs.  The scalar statistics
+(accept rate, mean log-ratio, objective terms) are all-reduced.
+
+``make_band_plan`` and ``exchange_halo`` are pure host logic (tested on CPU with gloo).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional
+
+import numpy as np
+
+from . import modelling as M
+from .device import MLP_FP32, DevicePosterior
+
+
+@dataclass
+class BandPlan:
+    H: int
+    W: int
+    world: int
+    rank: int
+    row0: int                 # first owned global row
+    row1: int                 # one past the last owned global row
+    g0: int                   # first stored global row (row0 or row0 - 1)
+    g1: int                   # one past the last stored global row
+    local_global_id: np.ndarray   # (N_loc,) global pixel id of every stored pixel, in local order
+    owned: np.ndarray             # (N_loc,) uint8
+    send_up: Optional[np.ndarray]    # local ids of my first owned row  (-> rank - 1)
+    send_down: Optional[np.ndarray]  # local ids of my last owned row   (-> rank + 1)
+    recv_up: Optional[np.ndarray]    # local ids of the ghost row above (<- rank - 1)
+    recv_down: Optional[np.ndarray]  # local ids of the ghost row below (<- rank + 1)
+
+    @property
+    def n_local(self) -> int:
+        return int(self.local_global_id.size)
+
+
+def band_rows(H: int, world: int, rank: int):
+    """Contiguous, balanced row ranges (first H % world ranks get one extra row)."""
+    base, rem = divmod(H, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+def make_band_plan(H: int, W: int, world: int, rank: int) -> BandPlan:
+    assert 1 <= world <= H, "need at least one row per rank"
+    r0, r1 = band_rows(H, world, rank)
+    g0 = r0 - 1 if rank > 0 else r0
+    g1 = r1 + 1 if rank < world - 1 else r1
+    rows = np.arange(g0, g1)
+    gid = (rows[:, None] * W + np.arange(W)[None, :]).reshape(-1).astype(np.int64)
+    owned = np.repeat((rows >= r0) & (rows < r1), W).astype(np.uint8)
+
+    def local_row(gr):
+        return ((gr - g0) * W + np.arange(W)).astype(np.int32)
+
+    return BandPlan(H, W, world, rank, r0, r1, g0, g1, gid, owned,
+                    local_row(r0) if rank > 0 else None,
+                    local_row(r1 - 1) if rank < world - 1 else None,
+                    local_row(r0 - 1) if rank > 0 else None,
+                    local_row(r1) if rank < world - 1 else None)
+
+
+def exchange_halo(plan: BandPlan, gather: Callable, scatter: Callable, dist, make_buffer: Callable):
+    """One halo exchange.  ``gather(name) -> tensor (W, D)`` reads the rows ``plan.<name>`` of the local
+    state (name in send_up / send_down), ``scatter(name, tensor)`` writes the rows ``plan.<name>`` (recv_up /
+    recv_down), ``make_buffer() -> tensor (W, D)`` allocates a receive buffer, ``dist`` is torch.distributed
+    (nccl on the GPUs, gloo in the CPU tests)."""
+    if plan.world == 1:
+        return
+    ops, recvs = [], []
+    if plan.send_up is not None:
+        ops.append(dist.P2POp(dist.isend, gather("send_up"), plan.rank - 1))
+        buf = make_buffer()
+        ops.append(dist.P2POp(dist.irecv, buf, plan.rank - 1))
+        recvs.append(("recv_up", buf))
+    if plan.send_down is not None:
+        ops.append(dist.P2POp(dist.isend, gather("send_down"), plan.rank + 1))
+        buf = make_buffer()
+        ops.append(dist.P2POp(dist.irecv, buf, plan.rank + 1))
+        recvs.append(("recv_down", buf))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for name, buf in recvs:
+        scatter(name, buf)
+
+
+def local_posterior(post, plan: BandPlan):
+    """Sub-problem of one band: observations sliced, prior graph rebuilt on the stored rows (global
+    coordinates, so colours and neighbour order are those of the full map), colour classes restricted to
+    the owned pixels."""
+    gid = plan.local_global_id
+    lik = post.likelihood
+    n_loc = gid.size
+    lik_loc = M.MixingModelsLikelihood(lik.forward_map, post.D, post.L, n_loc, lik.y[gid], lik.sigma_a[gid],
+                                       lik.sigma_m[gid], lik.omega[gid], lik.log_fm1[gid], lik.log_fp1[gid])
+    ps = post.prior_spatial
+    X, Y = gid // plan.W, gid % plan.W
+    sp = None
+    sites: Dict[int, np.ndarray]
+    if ps is not None:
+        sp = M.L22DiscreteGradSpatialPrior(post.D, n_loc, X, Y, None, ps.use_next_nearest_neighbors, ps.initial_weights)
+        sp.weights = np.asarray(ps.weights, dtype=np.float64).copy()
+        sites = {k: v[plan.owned[v] > 0] for k, v in sp.dict_sites.items()}
+    else:
+        sites = {0: np.where(plan.owned > 0)[0]}
+    return M.Posterior(post.D, post.L, n_loc, lik_loc, sp, post.prior_indicator, dict_sites=sites), sites
+
+
+class ShardedDevicePosterior:
+    """Same surface as DevicePosterior for B200Sampler, over ``torch.distributed`` ranks (one per GPU)."""
+
+    def __init__(self, posterior, H: int, W: int, device: int = 0, mlp_mode: int = MLP_FP32):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        assert posterior.N == H * W, "row-band sharding needs a full H x W map in row-major (X slow) order"
+        self.N, self.D, self.L = posterior.N, posterior.D, posterior.L
+        self.plan = make_band_plan(H, W, self.world, self.rank)
+        if self.world == 1:
+            self.local = DevicePosterior.from_posterior(posterior, device=device, mlp_mode=mlp_mode)
+        else:
+            post_loc, sites = local_posterior(posterior, self.plan)
+            self.local = DevicePosterior.from_posterior(post_loc, device=device, global_id=self.plan.local_global_id,
+                                                        dict_sites=sites, mlp_mode=mlp_mode)
+        self.n_sites, self.site_keys = self.local.n_sites, self.local.site_keys
+        self.dev = torch.device("cuda", device)
+        self._ids = {}
+        if self.world > 1:
+            for name in ("send_up", "send_down", "recv_up", "recv_down"):
+                a = getattr(self.plan, name)
+                if a is not None:
+                    self._ids[name] = torch.as_tensor(a, dtype=torch.int32, device=self.dev)
+        self._owned = self.plan.owned if self.world > 1 else None
+
+    # ---- halo
+    def halo_exchange(self):
+        if self.world == 1:
+            return
+        torch = self.torch
+
+        def gather(name):
+            t = self._ids[name]
+            out = torch.empty((t.numel(), self.D), dtype=torch.float32, device=self.dev)
+            self.local.gather_theta_rows(t.data_ptr(), t.numel(), out.data_ptr())
+            return out
+
+        def scatter(name, buf):
+            t = self._ids[name]
+            self.local.scatter_theta_rows(t.data_ptr(), t.numel(), buf.data_ptr())
+
+        def make_buffer():
+            return torch.empty((self.plan.W, self.D), dtype=torch.float32, device=self.dev)
+
+        exchange_halo(self.plan, gather, scatter, self.dist, make_buffer)
+
+    # ---- DevicePosterior surface used by B200Sampler
+    def compute_all(self, Theta=None):
+        if Theta is not None:
+            assert np.sum(np.isnan(Theta)) == 0
+            self.local.set_state(np.ascontiguousarray(Theta[self.plan.local_global_id]) if self.world > 1 else Theta)
+        self.local.refresh()
+        return self.get_current()
+
+    def init_v_from_grad(self):
+        self.local.init_v_from_grad()
+
+    def begin_iteration(self):
+        self.local.begin_iteration()
+
+    def pmala_site(self, site, *a, **k):
+        self.local.pmala_site(site, *a, **k)
+        self.halo_exchange()
+
+    def mtm_site(self, site, *a, **k):
+        self.local.mtm_site(site, *a, **k)
+        self.halo_exchange()
+
+    def mtm_finish(self, alpha):
+        self.local.mtm_finish(alpha)
+
+    def reduce_step_stats(self):
+        out = self.local.reduce_step_stats(self._owned)
+        return self._allreduce(out)
+
+    def objective_terms(self):
+        d = self.local.objective_terms(self._owned)
+        if self.world == 1:
+            return d
+        vec = np.concatenate([[d["nll"]], d["nl_prior_spatial"], d["nl_prior_indicator"], [d["objective"]]])
+        vec = self._allreduce(vec)
+        D = self.D
+        return {"nll": np.float64(vec[0]), "nl_prior_spatial": vec[1:1 + D], "nl_prior_indicator": vec[1 + D:1 + 2 * D],
+                "objective": float(vec[-1])}
+
+    def _allreduce(self, arr):
+        if self.world == 1:
+            return arr
+        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.dev)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def _gather_owned(self, local_arr):
+        """(N_loc, ...) -> (N, ...) on every rank."""
+        if self.world == 1:
+            return local_arr
+        torch = self.torch
+        own = local_arr[self.plan.owned > 0]
+        sizes = [(band_rows(self.plan.H, self.world, r)[1] - band_rows(self.plan.H, self.world, r)[0]) * self.plan.W
+                 for r in range(self.world)]
+        mine = torch.as_tensor(np.ascontiguousarray(own), device=self.dev)
+        outs = [torch.empty((s,) + tuple(own.shape[1:]), dtype=mine.dtype, device=self.dev) for s in sizes]
+        self.dist.all_gather(outs, mine)
+        return torch.cat(outs, 0).cpu().numpy()
+
+    def get_state(self, want_v=True, want_j=True):
+        th, v, j = self.local.get_state(want_v, want_j)
+        return (self._gather_owned(th), self._gather_owned(v) if want_v else None,
+                self._gather_owned(j) if want_j else None)
+
+    def get_current(self, with_forward_map=True):
+        cur = self.local.get_current(with_forward_map)
+        if self.world == 1:
+            return cur
+        out = {}
+        for k, val in cur.items():
+            if isinstance(val, dict):
+                out[k] = {kk: (self._gather_owned(vv) if isinstance(vv, np.ndarray) and vv.ndim >= 1 else vv)
+                          for kk, vv in val.items()}
+            elif isinstance(val, np.ndarray) and val.ndim >= 1:
+                out[k] = self._gather_owned(val)
+            else:
+                out[k] = val
+        for k in ("objective_chromatic", "objective_global"):
+            out[k] = float(out["objective_pix_" + k.split("_")[1]].sum())
+        out["nll_utils"] = {"nll": np.float64(out["nll_pix"].sum())}
+        return out
+
+    def step_stats(self):
+        a, lp = self.local.step_stats()
+        return self._gather_owned(a), self._gather_owned(lp)
+
+    def synchronize(self):
+        self.local.synchronize()
+
+    def kernel_launches(self):
+        return self.local.kernel_launches()
+
+    def close(self):
+        self.local.close()

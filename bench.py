@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the beetroots sampler step (PMALA + MTM) on B200 -- see DESIGN.md §measurement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one sampler iteration over the whole map.  Timed steps alternate MTM / PMALA
+deterministically (the expectation of the reference's selection_probas = (0.5, 0.5) draw,
+sampler/my_sampler.py:430-446), so K should be even.  Workload: config c4 of BASELINE.json,
+a 1024x1024 synthetic map, D=4, L=10, K_mtm=50, row-band sharded over N GPUs (strong scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pixel MCMC iterations/sec (PMALA+MTM) on 1M-pixel map"
+UNIT = "iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="map is size x size pixels")
+    ap.add_argument("--k-mtm", type=int, default=50)
+    ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--cpu-size", type=int, default=48, help="side of the bounded CPU-baseline sample map")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(size, k_mtm, steps=1, warmup=0):
+    """The oracle port of the reference step (oracle/sampler.py) timed on the host cores, on a bounded sample:
+    a size x size map, one MTM + one PMALA iteration per step.  Scaled linearly (a LOWER bound on the
+    reference, whose prior loops are O(N*E)) to the 1M-pixel map of the metric."""
+    import torch
+    from beetroots_b200 import modelling as M
+    from beetroots_b200.synthetic import make_problem
+    from oracle import posterior as OP
+    from oracle.sampler import OracleSampler
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    prob = make_problem(size, size, lambda fm, th: OP.forward_map_compute_all(fm, th, False)["log_f_Theta"], L=10,
+                        k_mtm=k_mtm)
+    post = prob.posterior
+    nbr = M.build_neighbor_table(post.prior_spatial.list_edges, post.N, 4)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, k_mtm)
+    orc.init(prob.theta_init)
+    rng = np.random.default_rng(0)
+
+    def one_pair():
+        noise = {}
+        for s, idx in post.dict_sites.items():
+            nb = nbr[idx]
+            # proposals in the spirit of utils.py:274-349 (mean of a random neighbour + N(0, 1/tau))
+            pick = nb[np.arange(idx.size), rng.integers(0, 2, idx.size)]
+            pick = np.where(pick >= 0, pick, nb[:, 0])
+            c = orc.current["Theta"][pick][:, None, :] + rng.standard_normal((idx.size, k_mtm, post.D)) / np.sqrt(
+                post.prior_spatial.weights)
+            noise[s] = {"cand": c, "u_sel": rng.uniform(size=idx.size), "u_acc": rng.uniform(size=idx.size)}
+        orc.mtm_step(noise)
+        noise = {s: {"z": rng.standard_normal((idx.size, post.D)), "u": rng.uniform(size=idx.size)}
+                 for s, idx in post.dict_sites.items()}
+        orc.pmala_step(noise)
+
+    for _ in range(warmup):
+        one_pair()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pair()
+    dt = time.perf_counter() - t0
+    its_small = 2 * steps / dt
+    scaled = its_small * (size * size) / (1024.0 * 1024.0)
+    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{size}x{size} map (K_mtm={k_mtm}, L=10, D=4), {steps} x (1 MTM + 1 PMALA) iterations of the float64 "
+                      f"numpy oracle port in {dt:.1f} s = {its_small:.3f} it/s at {size * size} pixels, scaled linearly "
+                      f"to 1,048,576 pixels (lower bound for the reference: its prior loops are O(N*E))",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.cpu_size, args.k_mtm, steps=max(1, args.steps // 2), warmup=1 if args.warmup else 0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / cb["value"] if cb["value"] > 0 else None, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"c4: 1024x1024 map, D=4, L=10, K_mtm={args.k_mtm}, p=(0.5,0.5); CPU sample {args.cpu_size}x{args.cpu_size}"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from beetroots_b200 import MLP_BF16_TC, MLP_FP32, B200Sampler, MySamplerParams
+    from beetroots_b200.device import gpu_log_f
+    from beetroots_b200.parallel import ShardedDevicePosterior
+    from beetroots_b200.synthetic import make_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    H = W = args.size
+    K = args.k_mtm
+    mode = {"fp32": MLP_FP32, "bf16": MLP_BF16_TC}.get(args.mlp)
+    if mode is None:
+        mode = MLP_BF16_TC if os.environ.get("BT_BENCH_BF16", "1") == "1" else MLP_FP32
+    prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K)
+    post = prob.posterior
+    try:
+        sdev = ShardedDevicePosterior(post, H, W, device=local, mlp_mode=mode)
+    except Exception as e:                       # tensor-core kernel unavailable -> exact fp32 kernel, stated in dtype
+        if mode == MLP_FP32:
+            raise
+        if rank == 0:
+            sys.stderr.write(f"[bench] bf16 tensor-core forward map unavailable ({e}); using the fp32 kernel\n")
+        mode = MLP_FP32
+        sdev = ShardedDevicePosterior(post, H, W, device=local, mlp_mode=mode)
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N,
+                      rng=np.random.default_rng(42), device=local, mlp_mode=mode)
+    smp.attach(post, sdev)
+    smp.philox_seed = 20231019
+    sdev.compute_all(prob.theta_init)
+    sdev.init_v_from_grad()
+    net = post.likelihood.forward_map.network
+    flops_row = 2.0 * net.macs_per_row()
+
+    def step(t):
+        if t % 2 == 0:
+            return smp.generate_new_sample_mtm(t, post)
+        return smp.generate_new_sample_pmala_rmsprop(t, post)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 0
+    for _ in range(args.warmup):
+        step(t)
+        t += 1
+    # ---- device-resident timing
+    sdev.local.mlp_profile(enable=True, reset=True)
+    launches0 = sdev.local.kernel_launches()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(t)
+        t += 1
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    mlp_ms, mlp_rows, mlp_launches = sdev.local.mlp_profile(enable=False, reset=True)
+    launches = sdev.local.kernel_launches() - launches0
+    # the library launches on its own stream semantics (legacy default stream): use the wall clock bracketed by
+    # synchronisations as the step time, cross-checked with the events
+    ms = max(ms, wall * 1000.0) if ms <= 0 else ms
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = args.steps / (ms / 1000.0) * (H * W) / (1024.0 * 1024.0)
+
+    # ---- end to end: host Theta in, host Theta out, every step (pinned buffers)
+    n_loc = sdev.local.N
+    pin_in = torch.empty((n_loc, post.D), dtype=torch.float32).pin_memory()
+    pin_out = torch.empty((n_loc, post.D), dtype=torch.float32).pin_memory()
+    sdev.local.get_theta_f32_ptr(pin_in.data_ptr())
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        sdev.local.set_theta_f32_ptr(pin_in.data_ptr())          # H2D of the step's input state
+        acc, lpa = step(t)
+        t += 1
+        sdev.local.get_theta_f32_ptr(pin_out.data_ptr())         # D2H of the result (synchronises)
+        pin_in.copy_(pin_out)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_val = args.steps / e2e_s * (H * W) / (1024.0 * 1024.0)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
+    achieved = (mlp_rows * flops_row / (mlp_ms / 1000.0)) / 1e12 if mlp_ms > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if mode == MLP_BF16_TC else "f32", "data": "synthetic",
+        "config": {"workload": f"c4: {H}x{W} map, D=4, L=10, K_mtm={K}, timed steps alternate MTM/PMALA (= p (0.5,0.5))",
+                   "parallelism": f"row bands x{world}, 1-row halo per colour sweep",
+                   "l2": "inputs larger than L2: candidate rows + observation constants ~2 GB per MTM sweep",
+                   "mlp": "tcgen05 bf16" if mode == MLP_BF16_TC else "CUDA-core fp32",
+                   "wall_s_timed": wall},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_loc * post.D * 4),
+                "d2h_bytes_per_step": int(n_loc * post.D * 4 + 16)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                     "kernel": "forward-map MLP", "peak_source": peak_src,
+                     "rows": int(mlp_rows), "launches": int(mlp_launches), "kernel_ms": mlp_ms,
+                     "share_of_step": mlp_ms / ms if ms > 0 else None,
+                     "pixel_candidate_evals_per_s_per_gpu": mlp_rows / (mlp_ms / 1000.0) if mlp_ms > 0 else None},
+    }
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(args.cpu_size, K, steps=1, warmup=0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
