@@ -1,15 +1,441 @@
-// Forward map kernel, tcgen05 / TMEM bf16 variant (placeholder until the tensor-core kernel lands:
-// tc_build reports "not ready", so bt_set_mlp_mode(BT_MLP_BF16_TC) fails loudly).
+// Forward map kernel, tcgen05 / TMEM variant: bf16 operands, fp32 accumulation in tensor memory.
+//
+// Same function as mlp_simt_kernel (NeuralNetworkApprox.compute_all / evaluate_log,
+// modelling/forward_maps/neural_network_approx.py:107-122,152-305 + nnbma forward / vmap(jacfwd)).
+//
+// Persistent, warp-specialised, one CTA per SM.  A tile is 64 "columns" (a column = a row of
+// theta, or one of its S-1 forward-mode tangents).  GEMM orientation per dense block l:
+//     D[out feature (M=128), column (N=64)] = W_l[out, k] (A, K-major) x H[column, k] (B, K-major)
+//   * B = the dense-concat activations of the 64 columns, resident in shared memory for the whole
+//     tile: K-blocks of 64 features, each a [64 x 64] bf16 tile in the canonical K-major
+//     SWIZZLE_128B layout (8 KB) -> 21 blocks = 168 KB for 1296 features; never touches HBM;
+//   * A = weight tiles [128 x 64] bf16, pre-swizzled on the host into the exact shared-memory
+//     image and streamed from L2 by the bulk-copy engine (cp.async.bulk, 16 KB per tile) through
+//     a 3-stage mbarrier ring;
+//   * D = 4 accumulator slots of 64 TMEM columns; the epilogue warps drain slot s (tcgen05.ld ->
+//     bias + GELU(erf) / GELU' x tangent -> bf16 -> swizzled st.shared into B) while the MMA warp
+//     fills slot s+1.  Because the network is a dense concat, block l+1 starts on the K-blocks
+//     holding features of blocks < l before the epilogue of block l has finished.
+// Warp roles: warp 0 = weight producer, warp 1 = TMEM allocator + MMA issuer (one elected thread),
+// warps 4..11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).
 #pragma once
+#include <cuda_bf16.h>
+#include <vector>
 #include "common.cuh"
 #include "mlp_simt.cuh"
 
+#define TC_BN 64            // columns per tile (UMMA N)
+#define TC_BM 128           // output features per weight tile (UMMA M)
+#define TC_BK 64            // features per K-block (one 128-byte swizzle atom of bf16)
+#define TC_STAGES 3
+#define TC_SLOTS 4
+#define TC_THREADS 384
+#define TC_WTILE_BYTES (TC_BM * TC_BK * 2)
+#define TC_KB_BYTES (TC_BN * TC_BK * 2)
+#define TC_MAX_LAYERS (BT_MAX_BLOCKS + 1)
+
+struct TcLayer {
+    int in, nnew, n_mt, n_kb, first_new_kb, bias_off, is_out;
+};
+struct TcSched {
+    int n_layers, n_wtiles, act_kb, n_out;
+    TcLayer L[TC_MAX_LAYERS];
+    const uint16_t* wstream;
+    const float* bias;
+};
 struct TcNet {
     bool ready = false;
+    TcSched sched{};
+    void* d_w = nullptr;
+    void* d_b = nullptr;
+    size_t smem_bytes = 0;
 };
-static inline void tc_free(TcNet& t) { t.ready = false; }
-static inline int tc_build(TcNet& t, int, int, const int32_t*, const double* const*, const double* const*, const double*, int, double) {
+
+static inline void tc_free(TcNet& t) {
+    if (t.d_w) cudaFree(t.d_w);
+    if (t.d_b) cudaFree(t.d_b);
+    t = TcNet();
+}
+
+static inline uint16_t f32_to_bf16_rne(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    if ((x & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((x >> 16) | 0x40);
+    const uint32_t lsb = (x >> 16) & 1u;
+    x += 0x7fffu + lsb;
+    return (uint16_t)(x >> 16);
+}
+
+// byte offset of element (row r, k in [0,64)) inside a K-major SWIZZLE_128B tile (rows of 128 bytes,
+// 8-row groups of 1024 bytes, 16-byte chunk index XOR (r % 8))
+__host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t k) {
+    return (r >> 3) * 1024u + (r & 7u) * 128u + ((((k >> 3) ^ (r & 7u)) & 7u) << 4) + ((k & 7u) << 1);
+}
+
+// Build the bf16 weight stream + schedule.  Returns 0; t.ready tells whether the shapes fit.
+static inline int tc_build(TcNet& t, int n_feat0, int n_blocks, const int32_t* block_new, const double* const* weights,
+                           const double* const* biases, const double* w_out, int n_out, double out_scale) {
     t.ready = false;
+    if (n_blocks + 1 > TC_MAX_LAYERS || n_out > 32) return 0;
+    TcSched& s = t.sched;
+    memset(&s, 0, sizeof s);
+    s.n_layers = n_blocks + 1;
+    s.n_out = n_out;
+    int w = n_feat0, prev_in = 0, bias_off = 0, n_wtiles = 0;
+    for (int l = 0; l <= n_blocks; ++l) {
+        TcLayer& L = s.L[l];
+        L.in = w;
+        L.nnew = l < n_blocks ? block_new[l] : n_out;
+        L.is_out = l == n_blocks;
+        L.n_mt = (L.nnew + TC_BM - 1) / TC_BM;
+        L.n_kb = (L.in + TC_BK - 1) / TC_BK;
+        L.first_new_kb = l == 0 ? 0 : prev_in / TC_BK;
+        L.bias_off = bias_off;
+        bias_off += L.n_mt * TC_BM;
+        n_wtiles += L.n_mt * L.n_kb;
+        prev_in = w;
+        if (l < n_blocks) w += block_new[l];
+    }
+    s.n_wtiles = n_wtiles;
+    s.act_kb = s.L[n_blocks].n_kb;
+    const size_t smem = (size_t)s.act_kb * TC_KB_BYTES + (size_t)TC_STAGES * TC_WTILE_BYTES + 1024 + 1024;
+    if (smem > 227 * 1024) return 0;
+    t.smem_bytes = smem;
+    std::vector<uint16_t> ws((size_t)n_wtiles * TC_BM * TC_BK, 0);
+    std::vector<float> bs(bias_off, 0.f);
+    size_t tile = 0;
+    for (int l = 0; l <= n_blocks; ++l) {
+        const TcLayer& L = s.L[l];
+        const double* W = L.is_out ? w_out : weights[l];
+        const double sc = L.is_out ? out_scale : 1.0;
+        for (int o = 0; o < L.nnew && !L.is_out; ++o) bs[L.bias_off + o] = (float)biases[l][o];
+        for (int mt = 0; mt < L.n_mt; ++mt)
+            for (int kb = 0; kb < L.n_kb; ++kb, ++tile) {
+                uint16_t* dst = ws.data() + tile * TC_BM * TC_BK;
+                for (int r = 0; r < TC_BM; ++r) {
+                    const int o = mt * TC_BM + r;
+                    if (o >= L.nnew) continue;
+                    for (int kk = 0; kk < TC_BK; ++kk) {
+                        const int k = kb * TC_BK + kk;
+                        if (k >= L.in) continue;
+                        dst[sw128_offset(r, kk) / 2] = f32_to_bf16_rne((float)(sc * W[(size_t)o * L.in + k]));
+                    }
+                }
+            }
+    }
+    if (cudaMalloc(&t.d_w, ws.size() * 2) != cudaSuccess) return -1;
+    if (cudaMalloc(&t.d_b, bs.size() * 4 + 16) != cudaSuccess) return -1;
+    if (cudaMemcpy(t.d_w, ws.data(), ws.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    if (cudaMemcpy(t.d_b, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    s.wstream = (const uint16_t*)t.d_w;
+    s.bias = (const float*)t.d_b;
+    t.ready = true;
     return 0;
 }
-static inline int tc_launch(TcNet&, const FmapDev&, const NetDev&, const float*, int, float*, float*, int, cudaStream_t) { return -1; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] x B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address        bits [0,14)
+    d |= (uint64_t)1 << 16;                       // leading byte offset  bits [16,30)  (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                       // descriptor version 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st_bf16(uint8_t* base, uint32_t off, float x) {
+    *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// S = columns per row of theta: 1 (forward only) or 4 (primal + 3 tangents)
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ rows, int M, float* __restrict__ lf,
+              float* __restrict__ jac) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* act = smem;                                             // [act_kb][64 x 64 bf16, SW128]
+    uint8_t* wst = smem + (size_t)sch.act_kb * TC_KB_BYTES;          // [TC_STAGES][128 x 64 bf16, SW128]
+    uint8_t* misc = wst + TC_STAGES * TC_WTILE_BYTES;
+    float* x0s = reinterpret_cast<float*>(misc);                     // [64] theta_full[0] of every column
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 256);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + 256 + 64 * 8);
+    const uint32_t bar_full = smem_u32(bars + 0), bar_empty = smem_u32(bars + TC_STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + TC_SLOTS);
+    const uint32_t bar_lready = smem_u32(bars + 2 * TC_STAGES + 2 * TC_SLOTS);   // [n_layers]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int P = TC_BN / S;                                     // rows of theta per tile
+    const int ntiles = (M + P - 1) / P;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+        mbar_init(bar_lready, 8);
+        for (int l = 1; l < sch.n_layers; ++l) mbar_init(bar_lready + 8 * l, 8 * sch.L[l - 1].n_mt);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // zero the activation buffer once: padded / not-yet-written features must be finite (they meet zero weights)
+        uint4* a4 = reinterpret_cast<uint4*>(act);
+        const int n16 = sch.act_kb * TC_KB_BYTES / 16;
+        for (int i = threadIdx.x; i < n16; i += TC_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int i = 0; i < sch.n_wtiles; ++i, ++it) {
+                    const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+                    mbar_expect_tx(bar_full + 8 * stage, TC_WTILE_BYTES);
+                    bulk_g2s(smem_u32(wst + stage * TC_WTILE_BYTES), sch.wstream + (size_t)i * TC_BM * TC_BK, TC_WTILE_BYTES,
+                             bar_full + 8 * stage);
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128 (cute UMMA::InstrDescriptor)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t act_addr = smem_u32(act), wst_addr = smem_u32(wst);
+            uint32_t it = 0, q = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                for (int l = 0; l < sch.n_layers; ++l) {
+                    const TcLayer L = sch.L[l];
+                    bool waited = false;
+                    for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
+                        const uint32_t slot = q % TC_SLOTS;
+                        mbar_wait(bar_tempty + 8 * slot, ((q / TC_SLOTS) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + slot * TC_BN;
+                        for (int kb = 0; kb < L.n_kb; ++kb, ++it) {
+                            if (!waited && kb >= L.first_new_kb) {        // features written by the previous block
+                                mbar_wait(bar_lready + 8 * l, tcount & 1u);
+                                waited = true;
+                            }
+                            const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                            mbar_wait(bar_full + 8 * stage, ph);
+                            tc_fence_after();
+                            const int krem = L.in - kb * TC_BK;
+                            const int nks = krem >= TC_BK ? 4 : (krem + 15) / 16;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint64_t a_desc = umma_desc_sw128(wst_addr + stage * TC_WTILE_BYTES + ks * 32);
+                                const uint64_t b_desc = umma_desc_sw128(act_addr + kb * TC_KB_BYTES + ks * 32);
+                                umma_f16(d_tmem, a_desc, b_desc, idesc, (kb | ks) ? 1u : 0u);
+                            }
+                            umma_commit(bar_empty + 8 * stage);           // frees the weight stage when the MMAs retire
+                        }
+                        umma_commit(bar_tfull + 8 * slot);                // accumulator complete -> epilogue
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== prologue + epilogue (8 warps) =====================
+        const int ew = warp - 4, qd = ew & 3, h = ew >> 2;
+        uint32_t q = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");           // previous tile fully drained (x0s, act reuse)
+            if (ew < 2) {
+                // ---- polynomial expansion of the 64 columns -> features [0, F0)
+                const int col = ew * 32 + lane, p = col / S, s = col - p * S;
+                const int row = tile * P + p;
+                const bool valid = row < M;
+                float xf[BT_MAX_D + 1];
+#pragma unroll
+                for (int i = 0; i <= BT_MAX_D; ++i) xf[i] = (i < fm.d_full) ? fm.fixed[i] : 0.f;
+                if (valid) {
+#pragma unroll
+                    for (int d = 0; d < BT_MAX_D; ++d)
+                        if (d < fm.D) {
+                            const float v = rows[(size_t)row * fm.D + d];
+#pragma unroll
+                            for (int i = 0; i <= BT_MAX_D; ++i)
+                                if (i == fm.full_idx[d]) xf[i] += v;
+                        }
+                }
+                x0s[col] = xf[0];
+                const int tin = (S > 1 && s > 0) ? fm.tinput[s - 1] : -1;
+                for (int f = 0; f < net.F0; ++f) {
+                    float val;
+                    if (s == 0) {
+                        val = 1.f;
+                        for (int j = 0; j < net.order; ++j) {
+                            const int e = net.exps[f * net.order + j];
+                            if (e >= 0) {
+                                float xe = 0.f;
+#pragma unroll
+                                for (int i = 1; i <= BT_MAX_D; ++i) if (i == e + 1) xe = xf[i];
+                                val *= xe;
+                            }
+                        }
+                        val = (val - net.mean[f]) * net.inv_std[f];
+                    } else {
+                        val = 0.f;
+                        for (int j = 0; j < net.order; ++j) {
+                            if (net.exps[f * net.order + j] != tin) continue;
+                            float term = 1.f;
+                            for (int j2 = 0; j2 < net.order; ++j2) {
+                                const int e2 = net.exps[f * net.order + j2];
+                                if (j2 != j && e2 >= 0) {
+                                    float xe = 0.f;
+#pragma unroll
+                                    for (int i = 1; i <= BT_MAX_D; ++i) if (i == e2 + 1) xe = xf[i];
+                                    term *= xe;
+                                }
+                            }
+                            val += term;
+                        }
+                        val *= net.inv_std[f];
+                    }
+                    st_bf16(act, (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(col, f % TC_BK), valid ? val : 0.f);
+                }
+            }
+            fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
+            asm volatile("bar.sync 1, 256;" ::: "memory");           // x0s visible to every epilogue warp
+            if (lane == 0) mbar_arrive(bar_lready);                   // inputs of block 0 ready
+
+            for (int l = 0; l < sch.n_layers; ++l) {
+                const TcLayer L = sch.L[l];
+                for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
+                    const uint32_t slot = q % TC_SLOTS;
+                    mbar_wait(bar_tfull + 8 * slot, (q / TC_SLOTS) & 1u);
+                    tc_fence_after();
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + slot * TC_BN + h * 32, v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // accumulator slot free again
+                    const int f = mt * TC_BM + qd * 32 + lane;           // output feature of this thread
+                    if (!L.is_out) {
+                        const bool live = f < L.nnew;
+                        const float b = live ? __ldg(sch.bias + L.bias_off + f) : 0.f;
+                        const uint32_t k = (uint32_t)(L.in + f);
+                        const uint32_t kbase = (k / TC_BK) * TC_KB_BYTES, kk = k % TC_BK;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float val;
+                            if (S == 1) {
+                                val = gelu_f(v[j] + b);
+                            } else {
+                                const int jp = j - (j % S);                 // primal column of this row of theta
+                                const float pre = v[jp] + b;
+                                val = (j % S == 0) ? gelu_f(pre) : gelu_prime_f(pre) * v[j];
+                            }
+                            if (live) st_bf16(act, kbase + sw128_offset((uint32_t)(h * 32 + j), kk), val);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_lready + 8 * (l + 1));
+                    } else if (f < sch.n_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = h * 32 + j, p = col / S, s = col - p * S;
+                            const int row = tile * P + p;
+                            if (row < M) {
+                                if (s == 0) lf[(size_t)row * sch.n_out + f] = v[j] + x0s[col];
+                                else jac[((size_t)row * (S - 1) + (s - 1)) * sch.n_out + f] = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+static inline int tc_launch(TcNet& t, const FmapDev& fm, const NetDev& net, const float* rows, int M, float* lf, float* jac,
+                            int sm_count, cudaStream_t stream) {
+    if (!t.ready) return -1;
+    const int S = jac ? 1 + fm.T : 1;
+    if (S != 1 && S != 4) return -2;
+    const int P = TC_BN / S;
+    const int ntiles = (M + P - 1) / P;
+    const int grid = ntiles < sm_count ? ntiles : sm_count;
+    if (S == 1) {
+        if (cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes) != cudaSuccess) return -3;
+        mlp_tc_kernel<1><<<grid, TC_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
+    } else {
+        if (cudaFuncSetAttribute(mlp_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes) != cudaSuccess) return -3;
+        mlp_tc_kernel<4><<<grid, TC_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
+    }
+    return 0;
+}
