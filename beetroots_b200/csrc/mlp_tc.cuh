@@ -36,12 +36,21 @@
 
 struct TcLayer {
     int in, nnew, n_mt, n_kb, first_new_kb, bias_off, is_out;
+    int w_off;      // offset (in 1 KB units) of this layer's first weight tile in the stream
 };
+// bytes of weight tile (layer L, M-tile mt): only the 8-row groups holding live output features are streamed;
+// the rest of the 128-row stage keeps (finite) data of earlier tiles and feeds accumulator lanes nobody reads.
+__host__ __device__ __forceinline__ int tc_tile_kb(const TcLayer& L, int mt) {
+    int rows = L.nnew - mt * TC_BM;
+    rows = rows > TC_BM ? TC_BM : rows;
+    return (rows + 7) / 8;                      // 1 KB per 8-row group (8 rows x 64 k x 2 B)
+}
 struct TcSched {
     int n_layers, n_wtiles, act_kb, n_out;
     TcLayer L[TC_MAX_LAYERS];
     const uint16_t* wstream;
     const float* bias;
+    long long* dbg;       // optional timeline buffer (BT_TC_DEBUG=1): [0..63] MMA thread, [64..127] epilogue warp 4
 };
 struct TcNet {
     bool ready = false;
@@ -81,7 +90,7 @@ static inline int tc_build(TcNet& t, int n_feat0, int n_blocks, const int32_t* b
     memset(&s, 0, sizeof s);
     s.n_layers = n_blocks + 1;
     s.n_out = n_out;
-    int w = n_feat0, prev_in = 0, bias_off = 0, n_wtiles = 0;
+    int w = n_feat0, prev_in = 0, bias_off = 0, n_wtiles = 0, stream_kb = 0;
     for (int l = 0; l <= n_blocks; ++l) {
         TcLayer& L = s.L[l];
         L.in = w;
@@ -93,25 +102,28 @@ static inline int tc_build(TcNet& t, int n_feat0, int n_blocks, const int32_t* b
         L.bias_off = bias_off;
         bias_off += L.n_mt * TC_BM;
         n_wtiles += L.n_mt * L.n_kb;
+        L.w_off = stream_kb;
+        for (int mt = 0; mt < L.n_mt; ++mt) stream_kb += tc_tile_kb(L, mt) * L.n_kb;
         prev_in = w;
         if (l < n_blocks) w += block_new[l];
     }
     s.n_wtiles = n_wtiles;
     s.act_kb = s.L[n_blocks].n_kb;
-    const size_t smem = (size_t)s.act_kb * TC_KB_BYTES + (size_t)TC_STAGES * TC_WTILE_BYTES + 1024 + 1024;
+    const size_t smem = (size_t)s.act_kb * TC_KB_BYTES + (size_t)TC_STAGES * TC_WTILE_BYTES + 1024 + 4096 + 1024;
+    if (n_feat0 > 64) return 0;
     if (smem > 227 * 1024) return 0;
     t.smem_bytes = smem;
-    std::vector<uint16_t> ws((size_t)n_wtiles * TC_BM * TC_BK, 0);
+    std::vector<uint16_t> ws((size_t)stream_kb * 512, 0);
     std::vector<float> bs(bias_off, 0.f);
-    size_t tile = 0;
+    size_t pos_kb = 0;
     for (int l = 0; l <= n_blocks; ++l) {
         const TcLayer& L = s.L[l];
         const double* W = L.is_out ? w_out : weights[l];
         const double sc = L.is_out ? out_scale : 1.0;
         for (int o = 0; o < L.nnew && !L.is_out; ++o) bs[L.bias_off + o] = (float)biases[l][o];
         for (int mt = 0; mt < L.n_mt; ++mt)
-            for (int kb = 0; kb < L.n_kb; ++kb, ++tile) {
-                uint16_t* dst = ws.data() + tile * TC_BM * TC_BK;
+            for (int kb = 0; kb < L.n_kb; ++kb, pos_kb += tc_tile_kb(L, mt)) {
+                uint16_t* dst = ws.data() + pos_kb * 512;
                 for (int r = 0; r < TC_BM; ++r) {
                     const int o = mt * TC_BM + r;
                     if (o >= L.nnew) continue;
@@ -202,6 +214,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// GELU(erf) through one MUFU: x Phi(x) ~= 0.5 x (1 + tanh(x (p0 + p1 x^2 + p2 x^4))), coefficients fitted (minimax
+// on [-8, 8]) to the erf form: max abs error 2.5e-5, far below the bf16 rounding of the stored activation
+// (the textbook two-term tanh form is 4.7e-4 off).  The tangent uses the exact derivative of this function.
+#define TC_G0 0.797507884f
+#define TC_G1 0.0370056460f
+#define TC_G2 -3.51516792e-4f
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gelu_tc(float x) {
+    const float xc = fminf(fmaxf(x, -8.f), 8.f), x2 = xc * xc;
+    const float t = tanh_mufu(xc * fmaf(x2, fmaf(x2, TC_G2, TC_G1), TC_G0));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+__device__ __forceinline__ float gelu_prime_tc(float x) {
+    const float xc = fminf(fmaxf(x, -8.f), 8.f), x2 = xc * xc;
+    const float t = tanh_mufu(xc * fmaf(x2, fmaf(x2, TC_G2, TC_G1), TC_G0));
+    const float du = fmaf(x2, fmaf(x2, 5.f * TC_G2, 3.f * TC_G1), TC_G0);
+    return 0.5f * (1.f + t) + 0.5f * xc * (1.f - t * t) * du;
+}
 __device__ __forceinline__ void st_bf16(uint8_t* base, uint32_t off, float x) {
     *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(x);
 }
@@ -221,6 +256,10 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
     float* x0s = reinterpret_cast<float*>(misc);                     // [64] theta_full[0] of every column
     uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 256);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + 256 + 64 * 8);
+    float* xin_s = reinterpret_cast<float*>(misc + 1024);            // [BT_MAX_D + 1][64] full parameter vector per column
+    float* pmean_s = xin_s + (BT_MAX_D + 1) * TC_BN;                 // [F0] (F0 <= 64)
+    float* pistd_s = pmean_s + 64;                                   // [F0]
+    int* pexp_s = reinterpret_cast<int*>(pistd_s + 64);              // [F0][4] exponent table (-1 padded)
     const uint32_t bar_full = smem_u32(bars + 0), bar_empty = smem_u32(bars + TC_STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + TC_SLOTS);
     const uint32_t bar_lready = smem_u32(bars + 2 * TC_STAGES + 2 * TC_SLOTS);   // [n_layers]
@@ -238,9 +277,14 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
     }
     {   // zero the activation buffer once: padded / not-yet-written features must be finite (they meet zero weights)
         uint4* a4 = reinterpret_cast<uint4*>(act);
-        const int n16 = sch.act_kb * TC_KB_BYTES / 16;
+        const int n16 = (sch.act_kb * TC_KB_BYTES + TC_STAGES * TC_WTILE_BYTES) / 16;   // activations + weight stages
         for (int i = threadIdx.x; i < n16; i += TC_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
+    }
+    for (int i = threadIdx.x; i < net.F0; i += TC_THREADS) {
+        pmean_s[i] = net.mean[i];
+        pistd_s[i] = net.inv_std[i];
+        for (int j = 0; j < 4; ++j) pexp_s[i * 4 + j] = j < net.order ? net.exps[i * net.order + j] : -1;
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512));
@@ -256,12 +300,18 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int i = 0; i < sch.n_wtiles; ++i, ++it) {
-                    const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                    mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
-                    mbar_expect_tx(bar_full + 8 * stage, TC_WTILE_BYTES);
-                    bulk_g2s(smem_u32(wst + stage * TC_WTILE_BYTES), sch.wstream + (size_t)i * TC_BM * TC_BK, TC_WTILE_BYTES,
-                             bar_full + 8 * stage);
+                for (int l = 0; l < sch.n_layers; ++l) {
+                    const TcLayer L = sch.L[l];
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(sch.wstream) + (size_t)L.w_off * 1024;
+                    for (int mt = 0; mt < L.n_mt; ++mt) {
+                        const uint32_t bytes = (uint32_t)tc_tile_kb(L, mt) * 1024u;
+                        for (int kb = 0; kb < L.n_kb; ++kb, ++it, src += bytes) {
+                            const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                            mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+                            mbar_expect_tx(bar_full + 8 * stage, bytes);
+                            bulk_g2s(smem_u32(wst + stage * TC_WTILE_BYTES), src, bytes, bar_full + 8 * stage);
+                        }
+                    }
                 }
         }
     } else if (warp == 1) {
@@ -272,9 +322,12 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
             const uint32_t act_addr = smem_u32(act), wst_addr = smem_u32(wst);
             uint32_t it = 0, q = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                const bool rec = sch.dbg && blockIdx.x == 0 && tcount == 1;
+                if (rec) sch.dbg[0] = clock64();
                 for (int l = 0; l < sch.n_layers; ++l) {
                     const TcLayer L = sch.L[l];
                     bool waited = false;
+                    if (rec) sch.dbg[1 + 3 * l] = clock64();
                     for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
                         const uint32_t slot = q % TC_SLOTS;
                         mbar_wait(bar_tempty + 8 * slot, ((q / TC_SLOTS) & 1u) ^ 1u);
@@ -282,7 +335,9 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                         const uint32_t d_tmem = tmem_base + slot * TC_BN;
                         for (int kb = 0; kb < L.n_kb; ++kb, ++it) {
                             if (!waited && kb >= L.first_new_kb) {        // features written by the previous block
+                                if (rec) sch.dbg[2 + 3 * l] = clock64();
                                 mbar_wait(bar_lready + 8 * l, tcount & 1u);
+                                if (rec) sch.dbg[3 + 3 * l] = clock64();
                                 waited = true;
                             }
                             const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
@@ -300,23 +355,26 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                         umma_commit(bar_tfull + 8 * slot);                // accumulator complete -> epilogue
                     }
                 }
+                if (rec) sch.dbg[1 + 3 * sch.n_layers] = clock64();
             }
         }
     } else if (warp >= 4) {
         // ===================== prologue + epilogue (8 warps) =====================
         const int ew = warp - 4, qd = ew & 3, h = ew >> 2;
-        uint32_t q = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t q = 0, tcount_e = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount_e) {
+            const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == 0 && lane == 0;
+            if (rec) sch.dbg[64] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");           // previous tile fully drained (x0s, act reuse)
+            if (rec) sch.dbg[65] = clock64();
+            // ---- polynomial expansion of the 64 columns -> features [0, F0): 4 threads per column, F0/4 features each
             if (ew < 2) {
-                // ---- polynomial expansion of the 64 columns -> features [0, F0)
-                const int col = ew * 32 + lane, p = col / S, s = col - p * S;
+                const int col = ew * 32 + lane, p = col / S;
                 const int row = tile * P + p;
-                const bool valid = row < M;
                 float xf[BT_MAX_D + 1];
 #pragma unroll
                 for (int i = 0; i <= BT_MAX_D; ++i) xf[i] = (i < fm.d_full) ? fm.fixed[i] : 0.f;
-                if (valid) {
+                if (row < M) {
 #pragma unroll
                     for (int d = 0; d < BT_MAX_D; ++d)
                         if (d < fm.D) {
@@ -326,39 +384,26 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                                 if (i == fm.full_idx[d]) xf[i] += v;
                         }
                 }
+#pragma unroll
+                for (int i = 0; i <= BT_MAX_D; ++i) xin_s[i * TC_BN + col] = xf[i];
                 x0s[col] = xf[0];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            {
+                const int t256 = ew * 32 + lane, col = t256 & 63, fg = t256 >> 6;
+                const int p = col / S, s = col - p * S;
+                const bool valid = tile * P + p < M;
                 const int tin = (S > 1 && s > 0) ? fm.tinput[s - 1] : -1;
-                for (int f = 0; f < net.F0; ++f) {
+                for (int f = fg; f < net.F0; f += 4) {
+                    const int e0 = pexp_s[f * 4], e1 = pexp_s[f * 4 + 1], e2 = pexp_s[f * 4 + 2];
+                    const float a0 = e0 >= 0 ? xin_s[(e0 + 1) * TC_BN + col] : 1.f;
+                    const float a1 = e1 >= 0 ? xin_s[(e1 + 1) * TC_BN + col] : 1.f;
+                    const float a2 = e2 >= 0 ? xin_s[(e2 + 1) * TC_BN + col] : 1.f;
                     float val;
                     if (s == 0) {
-                        val = 1.f;
-                        for (int j = 0; j < net.order; ++j) {
-                            const int e = net.exps[f * net.order + j];
-                            if (e >= 0) {
-                                float xe = 0.f;
-#pragma unroll
-                                for (int i = 1; i <= BT_MAX_D; ++i) if (i == e + 1) xe = xf[i];
-                                val *= xe;
-                            }
-                        }
-                        val = (val - net.mean[f]) * net.inv_std[f];
-                    } else {
-                        val = 0.f;
-                        for (int j = 0; j < net.order; ++j) {
-                            if (net.exps[f * net.order + j] != tin) continue;
-                            float term = 1.f;
-                            for (int j2 = 0; j2 < net.order; ++j2) {
-                                const int e2 = net.exps[f * net.order + j2];
-                                if (j2 != j && e2 >= 0) {
-                                    float xe = 0.f;
-#pragma unroll
-                                    for (int i = 1; i <= BT_MAX_D; ++i) if (i == e2 + 1) xe = xf[i];
-                                    term *= xe;
-                                }
-                            }
-                            val += term;
-                        }
-                        val *= net.inv_std[f];
+                        val = (a0 * a1 * a2 - pmean_s[f]) * pistd_s[f];
+                    } else {        // directional derivative along NN input `tin` (order <= 3)
+                        val = ((e0 == tin ? a1 * a2 : 0.f) + (e1 == tin ? a0 * a2 : 0.f) + (e2 == tin ? a0 * a1 : 0.f)) * pistd_s[f];
                     }
                     st_bf16(act, (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(col, f % TC_BK), valid ? val : 0.f);
                 }
@@ -366,39 +411,52 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
             fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
             asm volatile("bar.sync 1, 256;" ::: "memory");           // x0s visible to every epilogue warp
             if (lane == 0) mbar_arrive(bar_lready);                   // inputs of block 0 ready
+            if (rec) sch.dbg[66] = clock64();
 
             for (int l = 0; l < sch.n_layers; ++l) {
                 const TcLayer L = sch.L[l];
                 for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
                     const uint32_t slot = q % TC_SLOTS;
+                    if (rec && mt == 0) sch.dbg[67 + 3 * l] = clock64();
                     mbar_wait(bar_tfull + 8 * slot, (q / TC_SLOTS) & 1u);
+                    if (rec && mt == 0) sch.dbg[68 + 3 * l] = clock64();
                     tc_fence_after();
+                    const int f = mt * TC_BM + qd * 32 + lane;           // output feature of this thread
+                    if (mt * TC_BM + qd * 32 >= L.nnew) {                // no live feature in this warp's 32 lanes
+                        if (lane == 0) {
+                            mbar_arrive(bar_tempty + 8 * slot);
+                            if (!L.is_out) mbar_arrive(bar_lready + 8 * (l + 1));
+                        }
+                        continue;
+                    }
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + slot * TC_BN + h * 32, v);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // accumulator slot free again
-                    const int f = mt * TC_BM + qd * 32 + lane;           // output feature of this thread
                     if (!L.is_out) {
                         const bool live = f < L.nnew;
                         const float b = live ? __ldg(sch.bias + L.bias_off + f) : 0.f;
                         const uint32_t k = (uint32_t)(L.in + f);
-                        const uint32_t kbase = (k / TC_BK) * TC_KB_BYTES, kk = k % TC_BK;
+                        const uint32_t kk = k % TC_BK, chunk = kk >> 3;
+                        uint8_t* dst = act + (k / TC_BK) * TC_KB_BYTES + ((kk & 7u) << 1) + h * 4096;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float val;
                             if (S == 1) {
-                                val = gelu_f(v[j] + b);
+                                val = gelu_tc(v[j] + b);
                             } else {
                                 const int jp = j - (j % S);                 // primal column of this row of theta
                                 const float pre = v[jp] + b;
-                                val = (j % S == 0) ? gelu_f(pre) : gelu_prime_f(pre) * v[j];
+                                val = (j % S == 0) ? gelu_tc(pre) : gelu_prime_tc(pre) * v[j];
                             }
-                            if (live) st_bf16(act, kbase + sw128_offset((uint32_t)(h * 32 + j), kk), val);
+                            // row n = h*32 + j of the K-block: (n>>3)*1024 + (n&7)*128 + ((chunk ^ (n&7)) << 4)
+                            if (live) st_bf16(dst, (uint32_t)((j >> 3) * 1024 + (j & 7) * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4), val);
                         }
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_lready + 8 * (l + 1));
+                        if (rec && mt == L.n_mt - 1) sch.dbg[69 + 3 * l] = clock64();
                     } else if (f < sch.n_out) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -427,15 +485,39 @@ static inline int tc_launch(TcNet& t, const FmapDev& fm, const NetDev& net, cons
     if (!t.ready) return -1;
     const int S = jac ? 1 + fm.T : 1;
     if (S != 1 && S != 4) return -2;
+    if (net.order > 3) return -4;
     const int P = TC_BN / S;
     const int ntiles = (M + P - 1) / P;
     const int grid = ntiles < sm_count ? ntiles : sm_count;
+    long long* dbg = nullptr;
+    static const bool want_dbg = getenv("BT_TC_DEBUG") != nullptr;
+    if (want_dbg && ntiles > 2 * sm_count) {
+        cudaMalloc(&dbg, 128 * sizeof(long long));
+        cudaMemset(dbg, 0, 128 * sizeof(long long));
+    }
+    t.sched.dbg = dbg;
     if (S == 1) {
         if (cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes) != cudaSuccess) return -3;
         mlp_tc_kernel<1><<<grid, TC_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
     } else {
         if (cudaFuncSetAttribute(mlp_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes) != cudaSuccess) return -3;
         mlp_tc_kernel<4><<<grid, TC_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
+    }
+    if (dbg) {
+        long long h[128];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        t.sched.dbg = nullptr;
+        const long long t0 = h[0];
+        fprintf(stderr, "[tc timeline S=%d M=%d] MMA thread (cycles since tile start): ", S, M);
+        for (int l = 0; l < t.sched.n_layers; ++l)
+            fprintf(stderr, "L%d start %lld wait %lld..%lld | ", l, h[1 + 3 * l] - t0, h[2 + 3 * l] - t0, h[3 + 3 * l] - t0);
+        fprintf(stderr, "end %lld\n[tc timeline] epilogue warp4: enter %lld prologue-start %lld prologue-done %lld | ",
+                h[1 + 3 * t.sched.n_layers] - t0, h[64] - t0, h[65] - t0, h[66] - t0);
+        for (int l = 0; l < t.sched.n_layers; ++l)
+            fprintf(stderr, "L%d wait %lld..%lld done %lld | ", l, h[67 + 3 * l] - t0, h[68 + 3 * l] - t0, h[69 + 3 * l] - t0);
+        fprintf(stderr, "\n");
     }
     return 0;
 }
