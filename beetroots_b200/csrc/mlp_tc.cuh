@@ -174,6 +174,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// multicast variants (thread-block cluster): the copy lands at the same shared-memory offset of every CTA in
+// ctaMask and performs complete_tx on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -244,7 +262,9 @@ __device__ __forceinline__ void st_bf16(uint8_t* base, uint32_t off, float x) {
 // ---------------------------------------------------------------------------------------------
 // S = columns per row of theta: 1 (forward only) or 4 (primal + 3 tangents)
 // ---------------------------------------------------------------------------------------------
-template <int S>
+// CS = thread-block cluster size: the CS CTAs of a cluster walk the weight stream in lock-step, each fetches 1/CS of
+// every weight tile from L2 and multicasts it to all of them (L2 -> SM traffic / CS).
+template <int S, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ rows, int M, float* __restrict__ lf,
               float* __restrict__ jac) {
@@ -267,9 +287,14 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int P = TC_BN / S;                                     // rows of theta per tile
     const int ntiles = (M + P - 1) / P;
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+    // lock-step tile loop: every CTA of a cluster runs the same number of iterations (tiles >= ntiles are empty)
+    const int n_ctile = (ntiles + CS - 1) / CS, ctile0 = blockIdx.x / CS, ctile_step = gridDim.x / CS;
+#define TC_TILE_LOOP(var) for (int ct_ = ctile0, var = ctile0 * CS + (int)crank; ct_ < n_ctile; ct_ += ctile_step, var += ctile_step * CS)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CS); }
         for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
         mbar_init(bar_lready, 8);
         for (int l = 1; l < sch.n_layers; ++l) mbar_init(bar_lready + 8 * l, 8 * sch.L[l - 1].n_mt);
@@ -292,6 +317,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();                                  // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -299,7 +325,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
         // ===================== weight producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            TC_TILE_LOOP(tile)
                 for (int l = 0; l < sch.n_layers; ++l) {
                     const TcLayer L = sch.L[l];
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(sch.wstream) + (size_t)L.w_off * 1024;
@@ -309,7 +335,13 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                             const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                             mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
                             mbar_expect_tx(bar_full + 8 * stage, bytes);
-                            bulk_g2s(smem_u32(wst + stage * TC_WTILE_BYTES), src, bytes, bar_full + 8 * stage);
+                            if (CS == 1) {
+                                bulk_g2s(smem_u32(wst + stage * TC_WTILE_BYTES), src, bytes, bar_full + 8 * stage);
+                            } else {
+                                const uint32_t part = bytes / CS;       // 1 KB groups / CS: multiple of 16 B
+                                bulk_g2s_mc(smem_u32(wst + stage * TC_WTILE_BYTES) + crank * part, src + crank * part, part,
+                                            bar_full + 8 * stage, cmask);
+                            }
                         }
                     }
                 }
@@ -320,8 +352,9 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128 (cute UMMA::InstrDescriptor)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t act_addr = smem_u32(act), wst_addr = smem_u32(wst);
+            const uint64_t desc_base = umma_desc_sw128(0);
             uint32_t it = 0, q = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            TC_TILE_LOOP(tile) {
                 const bool rec = sch.dbg && blockIdx.x == 0 && tcount == 1;
                 if (rec) sch.dbg[0] = clock64();
                 for (int l = 0; l < sch.n_layers; ++l) {
@@ -342,27 +375,29 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                             }
                             const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                             mbar_wait(bar_full + 8 * stage, ph);
-                            tc_fence_after();
                             const int krem = L.in - kb * TC_BK;
                             const int nks = krem >= TC_BK ? 4 : (krem + 15) / 16;
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const uint64_t a_desc = umma_desc_sw128(wst_addr + stage * TC_WTILE_BYTES + ks * 32);
-                                const uint64_t b_desc = umma_desc_sw128(act_addr + kb * TC_KB_BYTES + ks * 32);
-                                umma_f16(d_tmem, a_desc, b_desc, idesc, (kb | ks) ? 1u : 0u);
-                            }
-                            umma_commit(bar_empty + 8 * stage);           // frees the weight stage when the MMAs retire
+                            // descriptors differ only in the 14-bit start-address field (16-byte units): +2 per k-step of 32 B
+                            const uint64_t a_desc = desc_base + ((wst_addr + stage * TC_WTILE_BYTES) >> 4);
+                            const uint64_t b_desc = desc_base + ((act_addr + kb * TC_KB_BYTES) >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < nks) umma_f16(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+                            if (CS == 1) umma_commit(bar_empty + 8 * stage);   // frees the weight stage when the MMAs retire
+                            else umma_commit_mc(bar_empty + 8 * stage, cmask);  // ... in every CTA of the cluster
                         }
                         umma_commit(bar_tfull + 8 * slot);                // accumulator complete -> epilogue
                     }
                 }
                 if (rec) sch.dbg[1 + 3 * sch.n_layers] = clock64();
+                ++tcount;
             }
         }
     } else if (warp >= 4) {
         // ===================== prologue + epilogue (8 warps) =====================
         const int ew = warp - 4, qd = ew & 3, h = ew >> 2;
         uint32_t q = 0, tcount_e = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount_e) {
+        TC_TILE_LOOP(tile) {
             const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == 0 && lane == 0;
             if (rec) sch.dbg[64] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");           // previous tile fully drained (x0s, act reuse)
@@ -470,10 +505,13 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                     }
                 }
             }
+            ++tcount_e;
         }
     }
+#undef TC_TILE_LOOP
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -488,7 +526,6 @@ static inline int tc_launch(TcNet& t, const FmapDev& fm, const NetDev& net, cons
     if (net.order > 3) return -4;
     const int P = TC_BN / S;
     const int ntiles = (M + P - 1) / P;
-    const int grid = ntiles < sm_count ? ntiles : sm_count;
     long long* dbg = nullptr;
     static const bool want_dbg = getenv("BT_TC_DEBUG") != nullptr;
     if (want_dbg && ntiles > 2 * sm_count) {
@@ -496,13 +533,31 @@ static inline int tc_launch(TcNet& t, const FmapDev& fm, const NetDev& net, cons
         cudaMemset(dbg, 0, 128 * sizeof(long long));
     }
     t.sched.dbg = dbg;
-    if (S == 1) {
-        if (cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes) != cudaSuccess) return -3;
-        mlp_tc_kernel<1><<<grid, TC_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
-    } else {
-        if (cudaFuncSetAttribute(mlp_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes) != cudaSuccess) return -3;
-        mlp_tc_kernel<4><<<grid, TC_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
-    }
+    static const int cs_env = getenv("BT_TC_CLUSTER") ? atoi(getenv("BT_TC_CLUSTER")) : 2;
+    const int CS = (cs_env == 1 || cs_env == 2 || cs_env == 4) ? cs_env : 2;
+    int g = ((ntiles + CS - 1) / CS) * CS;
+    const int gmax = (sm_count / CS) * CS;
+    if (g > gmax) g = gmax;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = t.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaSuccess;
+#define TC_LAUNCH(S_, CS_)                                                                                              \
+    do {                                                                                                                \
+        err = cudaFuncSetAttribute(mlp_tc_kernel<S_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes); \
+        if (err == cudaSuccess) err = cudaLaunchKernelEx(&cfg, mlp_tc_kernel<S_, CS_>, t.sched, net, fm, rows, M, lf, jac); \
+    } while (0)
+    if (S == 1) { if (CS == 1) TC_LAUNCH(1, 1); else if (CS == 2) TC_LAUNCH(1, 2); else TC_LAUNCH(1, 4); }
+    else        { if (CS == 1) TC_LAUNCH(4, 1); else if (CS == 2) TC_LAUNCH(4, 2); else TC_LAUNCH(4, 4); }
+#undef TC_LAUNCH
+    if (err != cudaSuccess) return -5;
     if (dbg) {
         long long h[128];
         cudaStreamSynchronize(stream);

@@ -1,0 +1,43 @@
+"""Run a short Philox chain on a row-band sharded map (torchrun, one rank per GPU) and dump the final state.
+Used by tests/test_gpu_multi.py to check that the chain is bit-identical for any number of GPUs."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import torch.distributed as dist
+
+from beetroots_b200 import MLP_BF16_TC, MLP_FP32, B200Sampler, MySamplerParams
+from beetroots_b200.device import gpu_log_f
+from beetroots_b200.parallel import ShardedDevicePosterior
+from beetroots_b200.synthetic import make_problem
+
+out, mode = sys.argv[1], sys.argv[2]
+H, W, K = 37, 24, 6
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+mlp = MLP_BF16_TC if mode == "bf16" else MLP_FP32
+prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K, use_next_nearest_neighbors=(mode == "fp32n8"))
+post = prob.posterior
+sdev = ShardedDevicePosterior(post, H, W, device=local, mlp_mode=mlp)
+smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N, device=local, mlp_mode=mlp)
+smp.attach(post, sdev)
+smp.philox_seed = 777
+sdev.compute_all(prob.theta_init)
+sdev.init_v_from_grad()
+stats = []
+for t in range(1, 7):
+    a = smp.generate_new_sample_mtm(t, post) if t % 2 == 0 else smp.generate_new_sample_pmala_rmsprop(t, post)
+    stats.append(a)
+th, v, j = sdev.get_state()
+terms = sdev.objective_terms()
+if int(os.environ.get("RANK", "0")) == 0:
+    np.savez(out, theta=th, v=v, j=j, stats=np.array(stats), objective=terms["objective"])
+    print("world", world, "accept/logpa per iteration", np.array(stats).round(4).tolist(), "objective", terms["objective"])
+if world > 1:
+    dist.destroy_process_group()
