@@ -28,7 +28,7 @@
 #define TC_BM 128           // output features per weight tile (UMMA M)
 #define TC_BK 64            // features per K-block (one 128-byte swizzle atom of bf16)
 #define TC_STAGES 3
-#define TC_SLOTS 4
+#define TC_SLOTS 8            // 4 units in flight x 2 split-K halves (one per MMA-issuing thread)
 #define TC_THREADS 384
 #define TC_WTILE_BYTES (TC_BM * TC_BK * 2)
 #define TC_KB_BYTES (TC_BN * TC_BK * 2)
@@ -164,6 +164,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// busy-poll variant for the single-thread pipeline roles (producer, MMA issuers): test_wait returns immediately,
+// try_wait parks the thread in hardware and pays a wake-up latency on every K-block
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -255,6 +269,11 @@ __device__ __forceinline__ float gelu_prime_tc(float x) {
     const float du = fmaf(x2, fmaf(x2, 5.f * TC_G2, 3.f * TC_G1), TC_G0);
     return 0.5f * (1.f + t) + 0.5f * xc * (1.f - t * t) * du;
 }
+// 32-bit shared-window address + st.shared (STS) instead of a generic 64-bit store: ~4 fewer instructions per element
+__device__ __forceinline__ void sts_bf16(uint32_t saddr, float x) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"(*reinterpret_cast<const uint16_t*>(&b)) : "memory");
+}
 __device__ __forceinline__ void st_bf16(uint8_t* base, uint32_t off, float x) {
     *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16_rn(x);
 }
@@ -333,7 +352,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                         const uint32_t bytes = (uint32_t)tc_tile_kb(L, mt) * 1024u;
                         for (int kb = 0; kb < L.n_kb; ++kb, ++it, src += bytes) {
                             const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                            mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+                            mbar_spin(bar_empty + 8 * stage, ph ^ 1u);
                             mbar_expect_tx(bar_full + 8 * stage, bytes);
                             if (CS == 1) {
                                 bulk_g2s(smem_u32(wst + stage * TC_WTILE_BYTES), src, bytes, bar_full + 8 * stage);
@@ -346,8 +365,13 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                     }
                 }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 2) {
+        // ===================== MMA issuers =====================
+        // Issuing a tcgen05.mma blocks the thread for the whole operand fetch (~85 cycles at M=128, N<=128) and the
+        // per-K-block barrier wait + commit (~260 cycles) cannot overlap with it, so ONE thread keeps the tensor core
+        // only ~50 % busy.  Two threads split every unit (block l, M-tile mt) along K: warp 1 takes the even K-blocks,
+        // warp 2 the odd ones, each into its own accumulator slot; the epilogue adds the two partial sums.
+        const int par = warp - 1;
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128 (cute UMMA::InstrDescriptor)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -355,18 +379,20 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
             const uint64_t desc_base = umma_desc_sw128(0);
             uint32_t it = 0, q = 0, tcount = 0;
             TC_TILE_LOOP(tile) {
-                const bool rec = sch.dbg && blockIdx.x == 0 && tcount == 1;
+                const bool rec = sch.dbg && blockIdx.x == 0 && tcount == 1 && par == 0;
                 if (rec) sch.dbg[0] = clock64();
                 for (int l = 0; l < sch.n_layers; ++l) {
                     const TcLayer L = sch.L[l];
                     bool waited = false;
                     if (rec) sch.dbg[1 + 3 * l] = clock64();
                     for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
-                        const uint32_t slot = q % TC_SLOTS;
-                        mbar_wait(bar_tempty + 8 * slot, ((q / TC_SLOTS) & 1u) ^ 1u);
+                        const uint32_t slot = 2u * (q % (TC_SLOTS / 2)) + (uint32_t)par;
+                        mbar_wait(bar_tempty + 8 * slot, ((q / (TC_SLOTS / 2)) & 1u) ^ 1u);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + slot * TC_BN;
+                        uint32_t acc = 0;                                  // first MMA of this half-unit overwrites
                         for (int kb = 0; kb < L.n_kb; ++kb, ++it) {
+                            if ((kb & 1) != par) continue;                 // the other issuer's K-block
                             if (!waited && kb >= L.first_new_kb) {        // features written by the previous block
                                 if (rec) sch.dbg[2 + 3 * l] = clock64();
                                 mbar_wait(bar_lready + 8 * l, tcount & 1u);
@@ -374,7 +400,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                                 waited = true;
                             }
                             const uint32_t stage = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                            mbar_wait(bar_full + 8 * stage, ph);
+                            mbar_spin(bar_full + 8 * stage, ph);
                             const int krem = L.in - kb * TC_BK;
                             const int nks = krem >= TC_BK ? 4 : (krem + 15) / 16;
                             // descriptors differ only in the 14-bit start-address field (16-byte units): +2 per k-step of 32 B
@@ -382,7 +408,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                             const uint64_t b_desc = desc_base + ((act_addr + kb * TC_KB_BYTES) >> 4);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
-                                if (ks < nks) umma_f16(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+                                if (ks < nks) { umma_f16(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, acc); acc = 1u; }
                             if (CS == 1) umma_commit(bar_empty + 8 * stage);   // frees the weight stage when the MMAs retire
                             else umma_commit_mc(bar_empty + 8 * stage, cmask);  // ... in every CTA of the cluster
                         }
@@ -451,42 +477,56 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
             for (int l = 0; l < sch.n_layers; ++l) {
                 const TcLayer L = sch.L[l];
                 for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
-                    const uint32_t slot = q % TC_SLOTS;
+                    const uint32_t slot = 2u * (q % (TC_SLOTS / 2));     // even-K partial sums; slot + 1 = odd-K partial sums
                     if (rec && mt == 0) sch.dbg[67 + 3 * l] = clock64();
-                    mbar_wait(bar_tfull + 8 * slot, (q / TC_SLOTS) & 1u);
+                    mbar_wait(bar_tfull + 8 * slot, (q / (TC_SLOTS / 2)) & 1u);
+                    mbar_wait(bar_tfull + 8 * (slot + 1), (q / (TC_SLOTS / 2)) & 1u);
                     if (rec && mt == 0) sch.dbg[68 + 3 * l] = clock64();
                     tc_fence_after();
                     const int f = mt * TC_BM + qd * 32 + lane;           // output feature of this thread
                     if (mt * TC_BM + qd * 32 >= L.nnew) {                // no live feature in this warp's 32 lanes
                         if (lane == 0) {
                             mbar_arrive(bar_tempty + 8 * slot);
+                            mbar_arrive(bar_tempty + 8 * (slot + 1));
                             if (!L.is_out) mbar_arrive(bar_lready + 8 * (l + 1));
                         }
                         continue;
                     }
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + slot * TC_BN + h * 32, v);
+                    if (L.n_kb > 1) {                                    // odd K-blocks were accumulated by the second issuer
+                        float w[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (slot + 1) * TC_BN + h * 32, w);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += w[j];
+                    }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // accumulator slot free again
+                    if (lane == 0) { mbar_arrive(bar_tempty + 8 * slot); mbar_arrive(bar_tempty + 8 * (slot + 1)); }   // slots free again
                     if (!L.is_out) {
                         const bool live = f < L.nnew;
                         const float b = live ? __ldg(sch.bias + L.bias_off + f) : 0.f;
                         const uint32_t k = (uint32_t)(L.in + f);
                         const uint32_t kk = k % TC_BK, chunk = kk >> 3;
-                        uint8_t* dst = act + (k / TC_BK) * TC_KB_BYTES + ((kk & 7u) << 1) + h * 4096;
+                        const uint32_t dst = smem_u32(act) + (k / TC_BK) * TC_KB_BYTES + ((kk & 7u) << 1) + h * 4096;
+                        // row n = h*32 + j of the K-block: (n>>3)*1024 + (n&7)*128 + ((chunk ^ (n&7)) << 4); the eight
+                        // swizzled chunk offsets are hoisted out of the element loop
+                        uint32_t swz[8];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float val;
-                            if (S == 1) {
-                                val = gelu_tc(v[j] + b);
-                            } else {
-                                const int jp = j - (j % S);                 // primal column of this row of theta
-                                const float pre = v[jp] + b;
-                                val = (j % S == 0) ? gelu_tc(pre) : gelu_prime_tc(pre) * v[j];
+                        for (int r = 0; r < 8; ++r) swz[r] = dst + (uint32_t)(r * 128) + ((chunk ^ (uint32_t)r) << 4);
+                        if (live) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float val;
+                                if (S == 1) {
+                                    val = gelu_tc(v[j] + b);
+                                } else {
+                                    const int jp = j - (j % S);             // primal column of this row of theta
+                                    const float pre = v[jp] + b;
+                                    val = (j % S == 0) ? gelu_tc(pre) : gelu_prime_tc(pre) * v[j];
+                                }
+                                sts_bf16(swz[j & 7] + (uint32_t)((j >> 3) * 1024), val);
                             }
-                            // row n = h*32 + j of the K-block: (n>>3)*1024 + (n&7)*128 + ((chunk ^ (n&7)) << 4)
-                            if (live) st_bf16(dst, (uint32_t)((j >> 3) * 1024 + (j & 7) * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4), val);
                         }
                         fence_proxy_async();
                         __syncwarp();
@@ -533,7 +573,7 @@ static inline int tc_launch(TcNet& t, const FmapDev& fm, const NetDev& net, cons
         cudaMemset(dbg, 0, 128 * sizeof(long long));
     }
     t.sched.dbg = dbg;
-    static const int cs_env = getenv("BT_TC_CLUSTER") ? atoi(getenv("BT_TC_CLUSTER")) : 2;
+    static const int cs_env = getenv("BT_TC_CLUSTER") ? atoi(getenv("BT_TC_CLUSTER")) : 1;   // weight multicast over a cluster: no gain measured
     const int CS = (cs_env == 1 || cs_env == 2 || cs_env == 4) ? cs_env : 2;
     int g = ((ntiles + CS - 1) / CS) * CS;
     const int gmax = (sm_count / CS) * CS;
