@@ -598,8 +598,8 @@ extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t,
         c->nbr, seed, t, site, c->gid, cd, c->rows);
     KLAUNCH(c);
     if (run_mlp(c, c->rows, (int)M, c->lf_rows, nullptr)) { free_tmp(c, tmp); return -1; }
-    const int warps_per_block = 4;
-    mtm_select_kernel<<<(n_pix + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, c->stream>>>(c->pr, c->fm,
+    const size_t mtm_smem = (size_t)MTM_WARPS * ((1u << c->max_degree) - 1u) * (BT_MAX_D + 1) * sizeof(float);
+    mtm_select_kernel<<<(n_pix + MTM_WARPS - 1) / MTM_WARPS, MTM_WARPS * 32, mtm_smem, c->stream>>>(c->pr, c->fm,
         n_pix, sp, c->D, c->L, K, c->max_degree, c->n_sites > 1, c->theta, c->nbr, c->obs, c->jt, c->rows, c->lf_rows, c->nl,
         seed, t, site, c->gid, usd, uad, c->accept, c->logpa, c->accepted_any);
     KLAUNCH(c);

@@ -306,62 +306,78 @@ __global__ void mtm_gen_kernel(PriorDev pr, int n_pix, const int* __restrict__ s
         if (d < D) out[d] = mean[d] * inv_m + z[d] * inv_m * rsqrtf(pr.tau_prop[d]);  // :336-345
 }
 
-// proposal log-density of one candidate (utils.py:419-495): sum_d log sum_S sqrt(tau_d) m exp(-(x_d-mu_Sd)^2 tau_d m^2)
-__device__ __forceinline__ float proposal_log_density(const PriorDev& pr, int D, int deg, const float (&nbv)[BT_MAX_DEGREE][BT_MAX_D],
-                                                      const float (&x)[BT_MAX_D]) {
-    float total = 0.f;
+// warp reductions
+__device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
-    for (int d = 0; d < BT_MAX_D; ++d) {
-        if (d >= D) continue;
-        const float tau = pr.tau_prop[d], st = sqrtf(tau);
-        // pass 1: max exponent, pass 2: weighted sum (numba_logsumexp_stable, utils.py:390-416)
-        float mx = -INFINITY;
-        for (uint32_t mask = 1; mask < (1u << deg); ++mask) {
-            float sum = 0.f;
-            int m = 0;
-            for (int j = 0; j < deg; ++j)
-                if ((mask >> j) & 1u) { sum += nbv[j][d]; ++m; }
-            const float diff = x[d] - sum / (float)m;
-            mx = fmaxf(mx, -diff * diff * tau * (float)(m * m));
-        }
-        float acc = 0.f;
-        for (uint32_t mask = 1; mask < (1u << deg); ++mask) {
-            float sum = 0.f;
-            int m = 0;
-            for (int j = 0; j < deg; ++j)
-                if ((mask >> j) & 1u) { sum += nbv[j][d]; ++m; }
-            const float diff = x[d] - sum / (float)m;
-            acc += st * (float)m * expf(-diff * diff * tau * (float)(m * m) - mx);
-        }
-        total += logf(acc) + mx;
-    }
-    return total;
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-// weights, selection, accept (my_sampler.py:1017-1178): one warp per pixel, lanes stride over candidates
-__global__ void mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_pix, int D, int L,
-                                  int K, int max_degree, int chromatic, float* __restrict__ theta,
-                                  const int* __restrict__ nbr, const ObsConst* __restrict__ obs,
-                                  int* __restrict__ jt, const float* __restrict__ cand_rows,
-                                  const float* __restrict__ lf_rows, float* __restrict__ nl_scratch,
-                                  uint64_t seed, int64_t t, int site, const int64_t* __restrict__ gid,
-                                  const float* __restrict__ usel_inject, const float* __restrict__ uacc_inject,
-                                  float* __restrict__ accept, float* __restrict__ logpa, uint8_t* __restrict__ accepted_any) {
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp_global >= n_pix) return;
-    const int i = warp_global, n = site_pix[i];
+// weights, selection, accept (my_sampler.py:1017-1178): one warp per pixel, lanes stride over candidates.
+// Shared memory per warp: the means mu_S (and sizes m_S) of all 2^deg - 1 non-empty neighbour subsets, computed once
+// per pixel and reused by every candidate for the proposal log-density
+//   log q(x) = sum_d log sum_S sqrt(tau_d) m_S exp(-(x_d - mu_Sd)^2 tau_d m_S^2)          (utils.py:419-495)
+#define MTM_WARPS 4
+__global__ void __launch_bounds__(MTM_WARPS * 32)
+mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_pix, int D, int L,
+                  int K, int max_degree, int chromatic, float* __restrict__ theta,
+                  const int* __restrict__ nbr, const ObsConst* __restrict__ obs,
+                  int* __restrict__ jt, const float* __restrict__ cand_rows,
+                  const float* __restrict__ lf_rows, float* __restrict__ nl_scratch,
+                  uint64_t seed, int64_t t, int site, const int64_t* __restrict__ gid,
+                  const float* __restrict__ usel_inject, const float* __restrict__ uacc_inject,
+                  float* __restrict__ accept, float* __restrict__ logpa, uint8_t* __restrict__ accepted_any) {
+    extern __shared__ float mtm_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * MTM_WARPS + wib;
+    if (i >= n_pix) return;
+    const int n = site_pix[i];
     const int K1 = K + 1;
+    const int nsub_max = (1 << max_degree) - 1;
+    float* mu = mtm_smem + (size_t)wib * nsub_max * (BT_MAX_D + 1);      // [nsub][D] then m_S in slot D
+    // ---- neighbours (registers; loops are unrolled over BT_MAX_DEGREE with guards)
     const int* nb = nbr + (size_t)n * max_degree;
     float nbv[BT_MAX_DEGREE][BT_MAX_D];
     int deg = 0;
-    for (int j = 0; j < max_degree; ++j) {
-        const int m = nb[j];
-        if (m < 0) continue;
 #pragma unroll
-        for (int d = 0; d < BT_MAX_D; ++d) nbv[deg][d] = (d < D) ? theta[(size_t)m * D + d] : 0.f;
-        ++deg;
+    for (int j = 0; j < BT_MAX_DEGREE; ++j) {
+        const int m = j < max_degree ? nb[j] : -1;
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) nbv[j][d] = 0.f;
+        if (m >= 0) {
+            // compact valid neighbours to the front (neighbour order = edge-list order)
+#pragma unroll
+            for (int jj = 0; jj < BT_MAX_DEGREE; ++jj)
+                if (jj == deg) {
+#pragma unroll
+                    for (int d = 0; d < BT_MAX_D; ++d) nbv[jj][d] = (d < D) ? theta[(size_t)m * D + d] : 0.f;
+                }
+            ++deg;
+        }
     }
+    const int nsub = (1 << deg) - 1;
+    for (int sidx = lane; sidx < nsub; sidx += 32) {
+        const uint32_t mask = (uint32_t)sidx + 1u;
+        float sum[BT_MAX_D];
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) sum[d] = 0.f;
+#pragma unroll
+        for (int j = 0; j < BT_MAX_DEGREE; ++j)
+            if ((mask >> j) & 1u) {
+#pragma unroll
+                for (int d = 0; d < BT_MAX_D; ++d) sum[d] += nbv[j][d];
+            }
+        const float m = (float)__popc(mask);
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) mu[sidx * (BT_MAX_D + 1) + d] = sum[d] / m;
+        mu[sidx * (BT_MAX_D + 1) + BT_MAX_D] = m;
+    }
+    __syncwarp();
     float* nl = nl_scratch + (size_t)i * K1;
     // ---- negative log weight of every candidate
     float mn = INFINITY;
@@ -373,62 +389,100 @@ __global__ void mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int*
         float val = lik_row<false>(fm, L, lf_rows + row * L, nullptr, obs + (size_t)n * L, dummy);  // :1021-1025
         if (pr.has_spatial) {                                                                      // posterior.py:96-103
             float sp = 0.f;
-            for (int j = 0; j < deg; ++j)
 #pragma unroll
-                for (int d = 0; d < BT_MAX_D; ++d)
-                    if (d < D) { const float df = x[d] - nbv[j][d]; sp = fmaf(pr.tau[d] * df, df, sp); }
+            for (int j = 0; j < BT_MAX_DEGREE; ++j)
+                if (j < deg) {
+#pragma unroll
+                    for (int d = 0; d < BT_MAX_D; ++d)
+                        if (d < D) { const float df = x[d] - nbv[j][d]; sp = fmaf(pr.tau[d] * df, df, sp); }
+                }
             val += sp;   // a colour class never holds all N pixels -> chromatic factor 1 (l22:103-105)
         }
         if (pr.has_indicator) val += indicator_terms(pr, D, x, dummy);                             // posterior.py:105-110
-        if (pr.has_spatial) val += proposal_log_density(pr, D, deg, nbv, x);                       // my_sampler.py:1093-1105
+        if (pr.has_spatial && nsub > 0) {                                                          // my_sampler.py:1093-1105
+            float total = 0.f;
+#pragma unroll
+            for (int d = 0; d < BT_MAX_D; ++d) {
+                if (d >= D) continue;
+                const float tau = pr.tau_prop[d], st = sqrtf(tau);
+                float mx = -INFINITY;                                   // numba_logsumexp_stable, utils.py:390-416
+                for (int sidx = 0; sidx < nsub; ++sidx) {
+                    const float m = mu[sidx * (BT_MAX_D + 1) + BT_MAX_D];
+                    const float diff = x[d] - mu[sidx * (BT_MAX_D + 1) + d];
+                    mx = fmaxf(mx, -diff * diff * tau * m * m);
+                }
+                float acc = 0.f;
+                for (int sidx = 0; sidx < nsub; ++sidx) {
+                    const float m = mu[sidx * (BT_MAX_D + 1) + BT_MAX_D];
+                    const float diff = x[d] - mu[sidx * (BT_MAX_D + 1) + d];
+                    acc += st * m * expf(-diff * diff * tau * m * m - mx);
+                }
+                total += logf(acc) + mx;
+            }
+            val += total;
+        } else if (pr.has_spatial) {
+            val = -INFINITY;            // isolated pixel: empty logsumexp
+        }
         nl[k] = val;
         mn = fminf(mn, val);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mn = warp_min(mn);
     __syncwarp();
-    // ---- lane 0: selection, ratio, accept.  The reference works with w_k = exp(-(nl_k - min nl))
-    // in float64 (:1107-1114); float32 would flush w_k to 0 beyond 87 nats, so everything is done
-    // in the log domain, relative to the best proposal (numerator, selection) and to the best
-    // remaining candidate (denominator).  A weight is dropped when float64 would have underflowed
-    // (nl_k - min > 745.13), which reproduces the reference's non-finite -> accepted quirk (:1156-1159).
+    // ---- selection, ratio, accept.  The reference works with w_k = exp(-(nl_k - min nl)) in float64 (:1107-1114);
+    // float32 would flush w_k to 0 beyond 87 nats, so everything is done in the log domain, relative to the best
+    // proposal (numerator, selection) and to the best remaining candidate (denominator).  A weight is dropped when
+    // float64 would have underflowed (nl_k - min > 745.13), which reproduces the reference's non-finite -> accepted
+    // quirk (:1156-1159).  All sums are warp reductions over candidates in a fixed order (deterministic).
+    const float F64_UNDERFLOW = 745.13f;
+    float dp = INFINITY;
+    for (int k = lane; k < K; k += 32) dp = fminf(dp, nl[k] - mn);
+    dp = warp_min(dp);
+    float s_prop = 0.f, s_all = 0.f, s_tot = 0.f;
+    for (int k = lane; k < K1; k += 32) {
+        const float dk = nl[k] - mn;
+        s_tot += expf(-dk);
+        if (k < K) {
+            const float w = expf(-(dk - dp));
+            s_all += w;
+            if (dk <= F64_UNDERFLOW) s_prop += w;
+        }
+    }
+    s_prop = warp_sum(s_prop); s_all = warp_sum(s_all); s_tot = warp_sum(s_tot);
+    const int64_t g = gid ? gid[n] : (int64_t)n;
+    // inverse-CDF selection with one uniform: Generator.choice == searchsorted(cdf, u, 'right') (:1123-1131)
+    const float us = usel_inject ? usel_inject[n] : bt_uniform(seed, t, BT_PURPOSE_MTM_USEL, site, g);
+    const float target = us * s_all;
+    int sel = K - 1;
+    float base = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        float w = (k < K) ? expf(-((nl[k] - mn) - dp)) : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {                          // inclusive scan in candidate order
+            const float up = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += up;
+        }
+        const float cum = base + w;
+        const unsigned hit = __ballot_sync(0xffffffffu, (k < K) && (cum > target));
+        if (hit) { sel = k0 + __ffs(hit) - 1; break; }
+        base += __shfl_sync(0xffffffffu, w, 31);
+    }
+    // denominator: sum over all candidates but the selected one (:1142-1144)
+    float d_o = INFINITY;
+    for (int k = lane; k < K1; k += 32)
+        if (k != sel) d_o = fminf(d_o, nl[k] - mn);
+    d_o = warp_min(d_o);
+    float s_den = 0.f;
+    for (int k = lane; k < K1; k += 32) {
+        const float dk = nl[k] - mn;
+        if (k != sel && dk <= F64_UNDERFLOW) s_den += expf(-(dk - d_o));
+    }
+    s_den = warp_sum(s_den);
     if (lane == 0) {
-        const int64_t g = gid ? gid[n] : (int64_t)n;
-        const float F64_UNDERFLOW = 745.13f;
-        float dp = INFINITY;                                         // best proposal, relative to the global min
-        for (int k = 0; k < K; ++k) dp = fminf(dp, nl[k] - mn);
-        float s_prop = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float dk = nl[k] - mn;
-            if (dk <= F64_UNDERFLOW) s_prop += expf(-(dk - dp));
-        }
         const float log_num = (s_prop > 0.f) ? logf(s_prop) - dp : -INFINITY;          // :1114
-        // inverse-CDF selection with one uniform: Generator.choice == searchsorted(cdf, u, 'right') (:1123-1131)
-        const float us = usel_inject ? usel_inject[n] : bt_uniform(seed, t, BT_PURPOSE_MTM_USEL, site, g);
-        float s_all = 0.f;                                           // softmax never underflows to all-zero (own max)
-        for (int k = 0; k < K; ++k) s_all += expf(-((nl[k] - mn) - dp));
-        const float target = us * s_all;
-        float cum = 0.f;
-        int sel = K - 1;
-        for (int k = 0; k < K; ++k) {
-            cum += expf(-((nl[k] - mn) - dp));
-            if (cum > target) { sel = k; break; }
-        }
-        // denominator: sum over all candidates but the selected one (:1142-1144)
-        float d_o = INFINITY;
-        for (int k = 0; k < K1; ++k)
-            if (k != sel) d_o = fminf(d_o, nl[k] - mn);
-        float s_den = 0.f;
-        for (int k = 0; k < K1; ++k) {
-            const float dk = nl[k] - mn;
-            if (k != sel && dk <= F64_UNDERFLOW) s_den += expf(-(dk - d_o));
-        }
         float log_den = (s_den > 0.f) ? logf(s_den) - d_o : -INFINITY;
-        // the reference forms the denominator as (sum of all weights) - w_sel in float64 (:1142-1144):
-        // when the other weights are below 2^-53 of the total the difference is exactly 0 -> log_rg = +inf
-        // -> replaced by 1e-15 (still accepted).  Reproduce that value.
-        float s_tot = 0.f;
-        for (int k = 0; k < K1; ++k) s_tot += expf(-(nl[k] - mn));           // >= 1: the best candidate has d = 0
+        // the reference forms the denominator as (sum of all weights) - w_sel in float64 (:1142-1144): when the other
+        // weights are below 2^-53 of the total the difference is exactly 0 -> log_rg = +inf -> replaced by 1e-15
         if (log_den < logf(s_tot) - 36.7368f) log_den = -INFINITY;
         float log_rg = log_num - log_den;
         if (!isfinite(log_rg)) log_rg = 1e-15f;                                        // :1156-1159
