@@ -262,6 +262,13 @@ def run_ours(args):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
     achieved = (mlp_rows * flops_row / (mlp_ms / 1000.0)) / 1e12 if mlp_ms > 0 else None
+    traffic = None
+    try:        # DRAM bytes per launch from the committed ncu --set full capture (per forward row x rows per launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_mlp_tc_traffic.json")))
+        if mode == MLP_BF16_TC and mlp_launches:
+            traffic = tj["dram_bytes_per_row"] * mlp_rows / mlp_launches
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -276,7 +283,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(n_loc * post.D * 4 + 16)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                     "algorithmic_flops_per_launch": flops_row * mlp_rows / mlp_launches if mlp_launches else None,
                      "kernel": "forward-map MLP", "peak_source": peak_src,
                      "rows": int(mlp_rows), "launches": int(mlp_launches), "kernel_ms": mlp_ms,
                      "share_of_step": mlp_ms / ms if ms > 0 else None,
