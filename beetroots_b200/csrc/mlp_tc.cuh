@@ -281,6 +281,47 @@ __device__ __forceinline__ void st_bf16(uint8_t* base, uint32_t off, float x) {
 // ---------------------------------------------------------------------------------------------
 // S = columns per row of theta: 1 (forward only) or 4 (primal + 3 tangents)
 // ---------------------------------------------------------------------------------------------
+// ---- prologue helpers: polynomial features of one column, 4 threads per column (fg = 0..3), features fg, fg+4, ...
+#define TC_FPT 16                  // features per thread (F0 <= 64)
+__device__ __forceinline__ float tc_sel(const float (&xf)[BT_MAX_D + 1], int e) {   // xf[e + 1], or 1 when e < 0
+    float r = 1.f;
+#pragma unroll
+    for (int i = 1; i <= BT_MAX_D; ++i) if (i == e + 1) r = xf[i];
+    return r;
+}
+// full parameter vector of the row of theta behind a column (global loads: issue early, consume late)
+__device__ __forceinline__ void tc_load_column(const FmapDev& fm, const float* __restrict__ rows, int M, int row,
+                                               float (&xf)[BT_MAX_D + 1]) {
+#pragma unroll
+    for (int i = 0; i <= BT_MAX_D; ++i) xf[i] = (i < fm.d_full) ? fm.fixed[i] : 0.f;
+    if (row < M) {
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d)
+            if (d < fm.D) {
+                const float v = __ldg(rows + (size_t)row * fm.D + d);
+#pragma unroll
+                for (int i = 0; i <= BT_MAX_D; ++i)
+                    if (i == fm.full_idx[d]) xf[i] += v;
+            }
+    }
+}
+// standardised monomials (s == 0) or their directional derivative along NN input tin (s > 0); order <= 3
+__device__ __forceinline__ void tc_poly_feats(const int* pexp_s, const float* pmean_s, const float* pistd_s, int F0, int fg,
+                                              int s, int tin, bool valid, const float (&xf)[BT_MAX_D + 1], float (&feat)[TC_FPT]) {
+#pragma unroll
+    for (int qf = 0; qf < TC_FPT; ++qf) {
+        const int f = fg + 4 * qf;
+        float val = 0.f;
+        if (f < F0 && valid) {
+            const int e0 = pexp_s[f * 4], e1 = pexp_s[f * 4 + 1], e2 = pexp_s[f * 4 + 2];
+            const float a0 = tc_sel(xf, e0), a1 = tc_sel(xf, e1), a2 = tc_sel(xf, e2);
+            if (s == 0) val = (a0 * a1 * a2 - pmean_s[f]) * pistd_s[f];
+            else val = ((e0 == tin ? a1 * a2 : 0.f) + (e1 == tin ? a0 * a2 : 0.f) + (e2 == tin ? a0 * a1 : 0.f)) * pistd_s[f];
+        }
+        feat[qf] = val;
+    }
+}
+
 // CS = thread-block cluster size: the CS CTAs of a cluster walk the weight stream in lock-step, each fetches 1/CS of
 // every weight tile from L2 and multicasts it to all of them (L2 -> SM traffic / CS).
 template <int S, int CS>
@@ -423,61 +464,49 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
         // ===================== prologue + epilogue (8 warps) =====================
         const int ew = warp - 4, qd = ew & 3, h = ew >> 2;
         uint32_t q = 0, tcount_e = 0;
+        // prologue work distribution: thread (pcol, fg) computes features fg, fg + 4, ... of column pcol
+        const int t256 = ew * 32 + lane, pcol = t256 & 63, fg = t256 >> 6;
+        const int pp = pcol / S, ps = pcol - pp * S;
+        const int ptin = (S > 1 && ps > 0) ? fm.tinput[ps - 1] : -1;
+        const uint32_t act_s = smem_u32(act);
+        float feat[TC_FPT], x0_next;
+        {
+            float xf0[BT_MAX_D + 1];
+            const int tile_first = ctile0 * CS + (int)crank;
+            tc_load_column(fm, rows, M, tile_first * P + pp, xf0);
+            tc_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, tile_first * P + pp < M, xf0, feat);
+            x0_next = xf0[0];
+        }
         TC_TILE_LOOP(tile) {
             const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == 0 && lane == 0;
             if (rec) sch.dbg[64] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");           // previous tile fully drained (x0s, act reuse)
             if (rec) sch.dbg[65] = clock64();
-            // ---- polynomial expansion of the 64 columns -> features [0, F0): 4 threads per column, F0/4 features each
-            if (ew < 2) {
-                const int col = ew * 32 + lane, p = col / S;
-                const int row = tile * P + p;
-                float xf[BT_MAX_D + 1];
+            // ---- input features of this tile (computed one tile ahead, see below) -> activation buffer
 #pragma unroll
-                for (int i = 0; i <= BT_MAX_D; ++i) xf[i] = (i < fm.d_full) ? fm.fixed[i] : 0.f;
-                if (row < M) {
-#pragma unroll
-                    for (int d = 0; d < BT_MAX_D; ++d)
-                        if (d < fm.D) {
-                            const float v = rows[(size_t)row * fm.D + d];
-#pragma unroll
-                            for (int i = 0; i <= BT_MAX_D; ++i)
-                                if (i == fm.full_idx[d]) xf[i] += v;
-                        }
-                }
-#pragma unroll
-                for (int i = 0; i <= BT_MAX_D; ++i) xin_s[i * TC_BN + col] = xf[i];
-                x0s[col] = xf[0];
+            for (int qf = 0; qf < TC_FPT; ++qf) {
+                const int f = fg + 4 * qf;
+                if (f < net.F0) sts_bf16(act_s + (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(pcol, f % TC_BK), feat[qf]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {
-                const int t256 = ew * 32 + lane, col = t256 & 63, fg = t256 >> 6;
-                const int p = col / S, s = col - p * S;
-                const bool valid = tile * P + p < M;
-                const int tin = (S > 1 && s > 0) ? fm.tinput[s - 1] : -1;
-                for (int f = fg; f < net.F0; f += 4) {
-                    const int e0 = pexp_s[f * 4], e1 = pexp_s[f * 4 + 1], e2 = pexp_s[f * 4 + 2];
-                    const float a0 = e0 >= 0 ? xin_s[(e0 + 1) * TC_BN + col] : 1.f;
-                    const float a1 = e1 >= 0 ? xin_s[(e1 + 1) * TC_BN + col] : 1.f;
-                    const float a2 = e2 >= 0 ? xin_s[(e2 + 1) * TC_BN + col] : 1.f;
-                    float val;
-                    if (s == 0) {
-                        val = (a0 * a1 * a2 - pmean_s[f]) * pistd_s[f];
-                    } else {        // directional derivative along NN input `tin` (order <= 3)
-                        val = ((e0 == tin ? a1 * a2 : 0.f) + (e1 == tin ? a0 * a2 : 0.f) + (e2 == tin ? a0 * a1 : 0.f)) * pistd_s[f];
-                    }
-                    st_bf16(act, (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(col, f % TC_BK), valid ? val : 0.f);
-                }
-            }
+            if (fg == 0) x0s[pcol] = x0_next;                          // read by the output-layer epilogue of this tile
             fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
-            asm volatile("bar.sync 1, 256;" ::: "memory");           // x0s visible to every epilogue warp
+            __syncwarp();
             if (lane == 0) mbar_arrive(bar_lready);                   // inputs of block 0 ready
             if (rec) sch.dbg[66] = clock64();
+            // ---- prefetch the rows of theta of my NEXT tile now (global latency hidden behind this tile's blocks) ...
+            float xf_n[BT_MAX_D + 1];
+            const int tile_next = tile + ctile_step * CS;
+            const bool valid_n = tile_next * P + pp < M;
+            tc_load_column(fm, rows, M, tile_next * P + pp, xf_n);
 
             for (int l = 0; l < sch.n_layers; ++l) {
                 const TcLayer L = sch.L[l];
                 for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
                     const uint32_t slot = 2u * (q % (TC_SLOTS / 2));     // even-K partial sums; slot + 1 = odd-K partial sums
+                    if (L.is_out && mt == 0) {                           // ... and turn them into features while the last block runs
+                        tc_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, valid_n, xf_n, feat);
+                        x0_next = xf_n[0];
+                    }
                     if (rec && mt == 0) sch.dbg[67 + 3 * l] = clock64();
                     mbar_wait(bar_tfull + 8 * slot, (q / (TC_SLOTS / 2)) & 1u);
                     mbar_wait(bar_tfull + 8 * (slot + 1), (q / (TC_SLOTS / 2)) & 1u);

@@ -159,8 +159,8 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
     uint8_t* misc = wst + TC_STAGES * TC_WTILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 256);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + 256 + 64 * 8);
-    float* xin_s = reinterpret_cast<float*>(misc + 1024);            // [BT_MAX_D + 1][64]
-    float* pmean_s = xin_s + (BT_MAX_D + 1) * 64;
+    float* x0s2 = reinterpret_cast<float*>(misc + 1024);             // [2][128] theta_full[0] of the pair-tile's columns (leader's copy is read)
+    float* pmean_s = x0s2 + (BT_MAX_D + 1) * 64;
     float* pistd_s = pmean_s + 64;
     int* pexp_s = reinterpret_cast<int*>(pistd_s + 64);
     // barriers (same offsets in both CTAs): full[3] empty[3] pfull[3] tfull[4] tempty[4] lready[n_layers]
@@ -293,57 +293,49 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
         const uint32_t act_dst = mapa_u32(smem_u32(act), (uint32_t)h);  // activation buffer of the CTA owning my 64 columns
         const uint32_t l_tempty = mapa_u32(bar_tempty, 0), l_lready = mapa_u32(bar_lready, 0);
         uint32_t q = 0, tcount_e = 0;
+        // prologue work distribution: thread (pcol, fg) computes features fg, fg + 4, ... of my column pcol
+        const int t256 = ew * 32 + lane, pcol = t256 & 63, fg = t256 >> 6;
+        const int gcol_p = (int)crank * 64 + pcol, pp = gcol_p / S, ps = gcol_p - pp * S;
+        const int ptin = (S > 1 && ps > 0) ? fm.tinput[ps - 1] : -1;
+        const uint32_t act_s = smem_u32(act);
+        float feat[TC_FPT], x0_cur;
+        const uint32_t x0_leader = mapa_u32(smem_u32(x0s2), 0);       // the output-layer epilogue runs in the leader CTA
+        {
+            float xf0[BT_MAX_D + 1];
+            tc_load_column(fm, rows, M, pt0 * P2 + pp, xf0);
+            tc_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, pt0 * P2 + pp < M, xf0, feat);
+            x0_cur = xf0[0];
+        }
         for (int pt = pt0; pt < n_ptiles; pt += pt_step, ++tcount_e) {
             const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == 0 && lane == 0;
             if (rec) sch.dbg[64] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (rec) sch.dbg[65] = clock64();
-            // ---- polynomial expansion of MY 64 columns (columns crank*64 .. +63 of the pair-tile) into my buffer
-            if (ew < 2) {
-                const int col = ew * 32 + lane, gcol = (int)crank * 64 + col, p = gcol / S;
-                const int row = pt * P2 + p;
-                float xf[BT_MAX_D + 1];
+            // ---- input features of MY 64 columns (computed one tile ahead, see below) -> my activation buffer
 #pragma unroll
-                for (int i = 0; i <= BT_MAX_D; ++i) xf[i] = (i < fm.d_full) ? fm.fixed[i] : 0.f;
-                if (row < M) {
-#pragma unroll
-                    for (int d = 0; d < BT_MAX_D; ++d)
-                        if (d < fm.D) {
-                            const float v = rows[(size_t)row * fm.D + d];
-#pragma unroll
-                            for (int i = 0; i <= BT_MAX_D; ++i)
-                                if (i == fm.full_idx[d]) xf[i] += v;
-                        }
-                }
-#pragma unroll
-                for (int i = 0; i <= BT_MAX_D; ++i) xin_s[i * 64 + col] = xf[i];
+            for (int qf = 0; qf < TC_FPT; ++qf) {
+                const int f = fg + 4 * qf;
+                if (f < net.F0) sts_bf16(act_s + (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(pcol, f % TC_BK), feat[qf]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {
-                const int t256 = ew * 32 + lane, col = t256 & 63, fg = t256 >> 6;
-                const int gcol = (int)crank * 64 + col, p = gcol / S, s = gcol - p * S;
-                const bool valid = pt * P2 + p < M;
-                const int tin = (S > 1 && s > 0) ? fm.tinput[s - 1] : -1;
-                for (int f = fg; f < net.F0; f += 4) {
-                    const int e0 = pexp_s[f * 4], e1 = pexp_s[f * 4 + 1], e2 = pexp_s[f * 4 + 2];
-                    const float a0 = e0 >= 0 ? xin_s[(e0 + 1) * 64 + col] : 1.f;
-                    const float a1 = e1 >= 0 ? xin_s[(e1 + 1) * 64 + col] : 1.f;
-                    const float a2 = e2 >= 0 ? xin_s[(e2 + 1) * 64 + col] : 1.f;
-                    float val;
-                    if (s == 0) val = (a0 * a1 * a2 - pmean_s[f]) * pistd_s[f];
-                    else val = ((e0 == tin ? a1 * a2 : 0.f) + (e1 == tin ? a0 * a2 : 0.f) + (e2 == tin ? a0 * a1 : 0.f)) * pistd_s[f];
-                    st_bf16(act, (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(col, f % TC_BK), valid ? val : 0.f);
-                }
-            }
+            if (fg == 0)                                                  // double-buffered: the peer may run one tile ahead
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(x0_leader + (uint32_t)(((tcount_e & 1u) * 128u + (uint32_t)gcol_p) * 4u)), "f"(x0_cur) : "memory");
             fence_proxy_async();                                          // local generic stores -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_lready);                 // inputs of block 0 ready (16 arrivals)
             if (rec) sch.dbg[66] = clock64();
+            // ---- prefetch the rows of theta of the NEXT pair-tile (latency hidden behind this tile's blocks)
+            float xf_n[BT_MAX_D + 1];
+            const int row_n = (pt + pt_step) * P2 + pp;
+            tc_load_column(fm, rows, M, row_n, xf_n);
 
             for (int l = 0; l < sch.n_layers; ++l) {
                 const Tc2Layer L = sch.L[l];
                 for (int mt = 0; mt < L.n_mt; ++mt, ++q) {
                     const uint32_t slot = 2u * (q % (TC2_SLOTS / 2));
+                    if (L.is_out && mt == 0) {                               // features of the next tile, while the last block runs
+                        tc_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, row_n < M, xf_n, feat);
+                        x0_cur = xf_n[0];
+                    }
                     if (rec && mt == 0) sch.dbg[67 + 3 * l] = clock64();
                     mbar_wait(bar_tfull + 8 * slot, (q / (TC2_SLOTS / 2)) & 1u);
                     mbar_wait(bar_tfull + 8 * (slot + 1), (q / (TC2_SLOTS / 2)) & 1u);
@@ -363,12 +355,14 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     const float b = (live && !L.is_out) ? __ldg(sch.bias + L.bias_off + f) : 0.f;
                     const uint32_t k = (uint32_t)(L.in + f);
                     const uint32_t kk = k % TC_BK, chunk = kk >> 3;
+                    // destination = activation buffer of the CTA that owns my 64 columns, addressed in the shared::cluster
+                    // window (works for my own buffer too): one store path, eight hoisted swizzle offsets
                     const uint32_t dst = act_dst + (k / TC_BK) * TC_KB_BYTES + ((kk & 7u) << 1);
-                    uint8_t* act_loc = act + (k / TC_BK) * TC_KB_BYTES + ((kk & 7u) << 1);
-                    const bool is_local = (uint32_t)h == crank;
+                    uint32_t swz[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) swz[r] = dst + (uint32_t)(r * 128) + ((chunk ^ (uint32_t)r) << 4);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {                   // my 64 columns = two 32-column TMEM loads
-                        if (rec && l == 1) sch.dbg[100 + half * 4] = clock64();
                         float v[32];
                         const uint32_t tcol = (uint32_t)(h * 64 + half * 32);
                         tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + slot * TC2_BN + tcol, v);
@@ -378,29 +372,25 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += w[j];
                         }
-                        if (rec && l == 1) sch.dbg[101 + half * 4] = clock64();
                         if (half == 1) {                                     // both halves read: the slots can be refilled
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) { mbar_arrive_cluster(l_tempty + 8 * slot); mbar_arrive_cluster(l_tempty + 8 * (slot + 1)); }
                         }
-                        if (rec && l == 1) sch.dbg[102 + half * 4] = clock64();
                         if (!L.is_out) {
+                            if (live) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float val;
-                                if (S == 1) {
-                                    val = gelu_tc(v[j] + b);
-                                } else {
-                                    const int jp = j - (j % S);
-                                    const float pre = v[jp] + b;
-                                    val = (j % S == 0) ? gelu_tc(pre) : gelu_prime_tc(pre) * v[j];
-                                }
-                                const int n = half * 32 + j;                 // column inside the owner's 64-column buffer
-                                const uint32_t off = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + ((chunk ^ (uint32_t)(n & 7)) << 4);
-                                if (live) {
-                                    if (is_local) st_bf16(act_loc, off, val);
-                                    else st_cluster_bf16(dst + off, val);
+                                for (int j = 0; j < 32; ++j) {
+                                    float val;
+                                    if (S == 1) {
+                                        val = gelu_tc(v[j] + b);
+                                    } else {
+                                        const int jp = j - (j % S);
+                                        const float pre = v[jp] + b;
+                                        val = (j % S == 0) ? gelu_tc(pre) : gelu_prime_tc(pre) * v[j];
+                                    }
+                                    const int n = half * 32 + j;             // column inside the owner's 64-column buffer
+                                    st_cluster_bf16(swz[n & 7] + (uint32_t)((n >> 3) * 1024), val);
                                 }
                             }
                         } else if (f < sch.n_out) {
@@ -410,11 +400,7 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                                 const int row = pt * P2 + p;
                                 if (row < M) {
                                     if (s == 0) {
-                                        float x0 = fm.fixed[0];
-#pragma unroll
-                                        for (int d = 0; d < BT_MAX_D; ++d)
-                                            if (d < fm.D && fm.full_idx[d] == 0) x0 += rows[(size_t)row * fm.D + d];
-                                        lf[(size_t)row * sch.n_out + f] = v[j] + x0;
+                                        lf[(size_t)row * sch.n_out + f] = v[j] + x0s2[(tcount_e & 1u) * 128u + (uint32_t)gcol];
                                     } else {
                                         jac[((size_t)row * (S - 1) + (s - 1)) * sch.n_out + f] = v[j];
                                     }
@@ -422,14 +408,12 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                             }
                         }
                     }
-                    if (rec && l == 1) sch.dbg[110] = clock64();
                     if (!L.is_out) {
                         // .shared::cluster / unqualified forms lower to MEMBAR.ALL.GPU, which stalls the whole SM for
                         // thousands of cycles; the CTA-scoped form orders this thread's generic stores (local and
                         // DSMEM) before the async-proxy reads that follow the barrier hand-off
                         fence_proxy_async();
                         __syncwarp();
-                        if (rec && l == 1) sch.dbg[111] = clock64();
                         if (lane == 0) mbar_arrive_cluster(l_lready + 8 * (l + 1));
                         if (rec && mt == L.n_mt - 1) sch.dbg[69 + 3 * l] = clock64();
                     }
@@ -487,8 +471,7 @@ static inline int tc2_launch(Tc2Net& t, const FmapDev& fm, const NetDev& net, co
                 h[64] - t0, h[65] - t0, h[66] - t0);
         for (int l = 0; l < t.sched.n_layers; ++l)
             fprintf(stderr, "L%d wait %lld..%lld done %lld | ", l, h[67 + 3 * l] - t0, h[68 + 3 * l] - t0, h[69 + 3 * l] - t0);
-        fprintf(stderr, "\n[tc2 epi L1] half0: start %lld ld-done %lld arrive-done %lld | half1: start %lld ld-done %lld arrive-done %lld | stores-done %lld fence-done %lld\n",
-                h[100] - h[100], h[101] - h[100], h[102] - h[100], h[104] - h[100], h[105] - h[100], h[106] - h[100], h[110] - h[100], h[111] - h[100]);
+        fprintf(stderr, "\n");
     }
     return 0;
 }

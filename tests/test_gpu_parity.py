@@ -391,3 +391,36 @@ def test_posterior_statistics_vs_oracle(lib, mode):
     width = lambda c: np.median(np.percentile(c, 84, axis=0) - np.percentile(c, 16, axis=0))      # noqa: E731
     wg = np.mean([width(c) for c in gs])
     assert 0.75 < wg / width(o) < 1.33
+
+
+def test_tensor_core_variants_agree(lib):
+    """The cta_group::2 kernel (experimental, BT_TC_VARIANT=2) must return exactly what the default single-CTA kernel
+    returns: same bf16 operands, same accumulation order per column."""
+    import subprocess
+    import sys
+    import os
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from beetroots_b200 import modelling as M, DevicePosterior, MLP_BF16_TC\n"
+        "from beetroots_b200.network import synthetic_weights\n"
+        "L, Mr = 10, 9001\n"
+        "net = synthetic_weights(0, L)\n"
+        "fm = M.NeuralNetworkApprox(net, {'kappa': None, 'P': None, 'radm': None, 'Avmax': None, 'angle': -1.5})\n"
+        "th = np.random.default_rng(1).uniform(-1.5, 1.5, size=(Mr, 4))\n"
+        "lik = M.MixingModelsLikelihood(fm, 4, L, Mr, np.ones((Mr, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)), a1=np.ones((1, L)))\n"
+        "dev = DevicePosterior.from_posterior(M.Posterior(4, L, Mr, lik, None, None), mlp_mode=MLP_BF16_TC)\n"
+        "out = dev.forward_map(th, compute_derivatives=True)\n"
+        "np.savez(sys.argv[1], lf=out['log_f_Theta'], jac=out['grad_log_f_Theta'])\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for variant in ("1", "2"):
+            path = os.path.join(tmp, f"v{variant}.npz")
+            env = dict(os.environ, BT_TC_VARIANT=variant)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(dict(np.load(path)))
+    assert np.array_equal(outs[0]["lf"], outs[1]["lf"])
+    assert np.array_equal(outs[0]["jac"], outs[1]["jac"])
