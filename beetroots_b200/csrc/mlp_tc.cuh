@@ -333,7 +333,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
     uint8_t* act = smem;                                             // [act_kb][64 x 64 bf16, SW128]
     uint8_t* wst = smem + (size_t)sch.act_kb * TC_KB_BYTES;          // [TC_STAGES][128 x 64 bf16, SW128]
     uint8_t* misc = wst + TC_STAGES * TC_WTILE_BYTES;
-    float* x0s = reinterpret_cast<float*>(misc);                     // [64] theta_full[0] of every column
+    float* x0s = reinterpret_cast<float*>(misc);                     // [2][64] theta_full[0] of every column (ping-pong over tiles)
     uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 256);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + 256 + 64 * 8);
     float* xin_s = reinterpret_cast<float*>(misc + 1024);            // [BT_MAX_D + 1][64] full parameter vector per column
@@ -477,22 +477,25 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
             tc_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, tile_first * P + pp < M, xf0, feat);
             x0_next = xf0[0];
         }
-        TC_TILE_LOOP(tile) {
-            const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == 0 && lane == 0;
-            if (rec) sch.dbg[64] = clock64();
-            asm volatile("bar.sync 1, 256;" ::: "memory");           // previous tile fully drained (x0s, act reuse)
-            if (rec) sch.dbg[65] = clock64();
-            // ---- input features of this tile (computed one tile ahead, see below) -> activation buffer
+        // Hand-over of the activation buffer between tiles: the input features of tile k+1 are written by each warp
+        // right after IT has seen the output-layer accumulators of tile k complete (all MMAs of tile k have then read
+        // the buffer), before it drains them -- so block 0 of the next tile overlaps with the output epilogue of this one.
+        auto publish_inputs = [&](uint32_t parity) {
 #pragma unroll
             for (int qf = 0; qf < TC_FPT; ++qf) {
                 const int f = fg + 4 * qf;
                 if (f < net.F0) sts_bf16(act_s + (uint32_t)(f / TC_BK) * TC_KB_BYTES + sw128_offset(pcol, f % TC_BK), feat[qf]);
             }
-            if (fg == 0) x0s[pcol] = x0_next;                          // read by the output-layer epilogue of this tile
+            if (fg == 0) x0s[parity * 64 + pcol] = x0_next;          // read by the output-layer epilogue of that tile
             fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_lready);                   // inputs of block 0 ready
-            if (rec) sch.dbg[66] = clock64();
+        };
+        if (ctile0 < n_ctile) publish_inputs(0);
+        TC_TILE_LOOP(tile) {
+            const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == 0 && lane == 0;
+            if (rec) sch.dbg[64] = sch.dbg[65] = sch.dbg[66] = clock64();
+            const bool has_next = ct_ + ctile_step < n_ctile;
             // ---- prefetch the rows of theta of my NEXT tile now (global latency hidden behind this tile's blocks) ...
             float xf_n[BT_MAX_D + 1];
             const int tile_next = tile + ctile_step * CS;
@@ -511,6 +514,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                     mbar_wait(bar_tfull + 8 * slot, (q / (TC_SLOTS / 2)) & 1u);
                     mbar_wait(bar_tfull + 8 * (slot + 1), (q / (TC_SLOTS / 2)) & 1u);
                     if (rec && mt == 0) sch.dbg[68 + 3 * l] = clock64();
+                    if (L.is_out && mt == L.n_mt - 1 && has_next) publish_inputs((tcount_e + 1u) & 1u);
                     tc_fence_after();
                     const int f = mt * TC_BM + qd * 32 + lane;           // output feature of this thread
                     if (mt * TC_BM + qd * 32 >= L.nnew) {                // no live feature in this warp's 32 lanes
@@ -567,7 +571,7 @@ mlp_tc_kernel(TcSched sch, NetDev net, FmapDev fm, const float* __restrict__ row
                             const int col = h * 32 + j, p = col / S, s = col - p * S;
                             const int row = tile * P + p;
                             if (row < M) {
-                                if (s == 0) lf[(size_t)row * sch.n_out + f] = v[j] + x0s[col];
+                                if (s == 0) lf[(size_t)row * sch.n_out + f] = v[j] + x0s[(tcount_e & 1u) * 64 + col];
                                 else jac[((size_t)row * (S - 1) + (s - 1)) * sch.n_out + f] = v[j];
                             }
                         }
