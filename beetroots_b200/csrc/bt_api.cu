@@ -53,6 +53,9 @@ struct bt_ctx {
     int* jt = nullptr;
     float *accept = nullptr, *logpa = nullptr;
     uint8_t* accepted_any = nullptr;
+    // online model checking accumulators (my_sampler.py:385-401)
+    float *mc_clppd = nullptr, *mc_pvy = nullptr, *mc_pvl = nullptr;
+    double mc_count = 0;
     // scratch (grown on demand)
     float *rows = nullptr, *lf_rows = nullptr, *jac_rows = nullptr, *nl = nullptr, *logq = nullptr, *objc = nullptr;
     size_t rows_cap = 0, jac_cap = 0;
@@ -136,7 +139,7 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
     tc2_free(c->tc2);
     void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
-                    c->tmpf, c->tmpd, c->owned_dev};
+                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -688,5 +691,51 @@ extern "C" int bt_debug_philox_mtm(bt_ctx* c, int site, int K, uint64_t seed, in
     CK(cudaMemcpyAsync(uacc_out, uad, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(cd); cudaFree(usd); cudaFree(uad);
+    return 0;
+}
+
+// ---- online model checking ---------------------------------------------------------------------------
+extern "C" int bt_model_check_reset(bt_ctx* c) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    const size_t nl = (size_t)c->N * c->L;
+    if (!c->mc_clppd) {
+        CK(cudaMalloc(&c->mc_clppd, nl * 4)); CK(cudaMalloc(&c->mc_pvy, nl * 4)); CK(cudaMalloc(&c->mc_pvl, (size_t)c->N * 4));
+    }
+    CK(cudaMemsetAsync(c->mc_clppd, 0, nl * 4, c->stream));
+    CK(cudaMemsetAsync(c->mc_pvy, 0, nl * 4, c->stream));
+    CK(cudaMemsetAsync(c->mc_pvl, 0, (size_t)c->N * 4, c->stream));
+    c->mc_count = 0;
+    return 0;
+}
+
+extern "C" int bt_model_check_update(bt_ctx* c, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject) {
+    READY(c);
+    REQUIRE((za_inject == nullptr) == (zm_inject == nullptr), "inject both noise arrays or none");
+    if (!c->mc_clppd && bt_model_check_reset(c)) return -1;
+    CK(cudaSetDevice(c->device));
+    std::vector<void*> tmp;
+    float *zad, *zmd;
+    const size_t nl = (size_t)c->N * c->L;
+    if (stage_inject(c, za_inject, nl, &zad, tmp) || stage_inject(c, zm_inject, nl, &zmd, tmp)) { free_tmp(c, tmp); return -1; }
+    model_check_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->N, c->L, c->lf_cache, c->obs, (float)c->mc_count, seed, t,
+                                                                   c->gid, zad, zmd, c->mc_clppd, c->mc_pvy, c->mc_pvl);
+    KLAUNCH(c);
+    c->mc_count += 1;
+    free_tmp(c, tmp);
+    return 0;
+}
+
+extern "C" int bt_model_check_get(bt_ctx* c, double* clppd, double* pval_y, double* pval_llh, int finalize) {
+    REQUIRE(c && c->mc_clppd, "model check not started");
+    CK(cudaSetDevice(c->device));
+    const size_t nl = (size_t)c->N * c->L;
+    if (clppd && d2h_to_double(c, clppd, c->mc_clppd, nl)) return -1;
+    if (pval_y) {
+        if (d2h_to_double(c, pval_y, c->mc_pvy, nl)) return -1;
+        if (finalize)                                  // _finalize_model_check_values, my_sampler.py:260-265
+            for (size_t i = 0; i < nl; ++i) if (pval_y[i] > 0.5) pval_y[i] = 1.0 - pval_y[i];
+    }
+    if (pval_llh && d2h_to_double(c, pval_llh, c->mc_pvl, c->N)) return -1;
     return 0;
 }

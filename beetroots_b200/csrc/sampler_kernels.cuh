@@ -531,6 +531,61 @@ __global__ void mtm_finish_kernel(PriorDev pr, FmapDev fm, int N, int D, int L, 
     accepted_any[n] = 0;
 }
 
+// ---- online model checking (my_sampler.py:158-214, sampling branch) ---------------------------------------------
+// Per saved iterate: draw a replicated observation y_rep = max(omega, eps_m f + eps_a)
+// (approx_censored_add_mult.py:268-280), evaluate its negative log-likelihood, and update the running means
+//   clppd[n,l]  <- mean of exp(-nll[n,l])                      (:169-170)
+//   p_y[n,l]    <- mean of [y_rep <= y]                        (:194-195)
+//   p_llh[n]    <- mean of [sum_l nll_rep >= sum_l nll]        (:199-203)
+// Everything is expressed in units of sigma_a like the rest of the likelihood (eps_a / sigma_a ~ N(0,1)).
+#define BT_PURPOSE_MCHK_A 7u
+#define BT_PURPOSE_MCHK_M 8u
+__global__ void model_check_kernel(int N, int L, const float* __restrict__ lf_cache, const ObsConst* __restrict__ obs,
+                                   float count, uint64_t seed, int64_t t, const int64_t* __restrict__ gid,
+                                   const float* __restrict__ za_inject, const float* __restrict__ zm_inject,
+                                   float* __restrict__ clppd, float* __restrict__ pvy, float* __restrict__ pvl) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int64_t g = gid ? gid[n] : (int64_t)n;
+    const float wgt_old = count / (count + 1.0f), wgt_new = 1.0f / (count + 1.0f);
+    float nll_sum = 0.f, nll_rep_sum = 0.f;
+    for (int l = 0; l < L; ++l) {
+        const float4* op = reinterpret_cast<const float4*>(obs + (size_t)n * L + l);
+        union { float4 v[3]; ObsConst o; } u;
+        u.v[0] = __ldg(op); u.v[1] = __ldg(op + 1); u.v[2] = __ldg(op + 2);
+        const float lf = lf_cache[(size_t)n * L + l];
+        float nll, dummy;
+        mixing_line<false>(lf, u.o, nll, dummy);
+        float za, zm;
+        if (za_inject) {
+            za = za_inject[(size_t)n * L + l];
+            zm = zm_inject[(size_t)n * L + l];
+        } else {
+            uint32_t r[4];
+            bt_philox(r, seed, t, BT_PURPOSE_MCHK_A, 0, g, (uint32_t)l);
+            box_muller(r[0], r[1], za, zm);
+        }
+        // y_rep / sigma_a = max(omega / sigma_a, eps_m f / sigma_a + eps_a / sigma_a)
+        const float r_f = expf(lf - u.o.lsa);
+        const float sm = sqrtf(u.o.sm2);
+        const float eps_m = expf(-0.5f * u.o.sm2 + sm * zm);                      // lognormal(-sigma_m^2/2, sigma_m)
+        const float yr_rep = fmaxf(u.o.wr, eps_m * r_f + za);
+        ObsConst o2 = u.o;
+        o2.yr = yr_rep;
+        // NB ln(y) is NOT refreshed: the reference replaces likelihood_rep.y only (my_sampler.py:176-177), so the
+        // multiplicative branch of the replicated likelihood keeps ln(y) of the original observation
+        o2.flags = (yr_rep <= u.o.wr ? 1u : 0u) | (yr_rep == u.o.wr ? 2u : 0u);
+        float nll_rep;
+        mixing_line<false>(lf, o2, nll_rep, dummy);
+        nll_sum += nll;
+        nll_rep_sum += nll_rep;
+        const size_t idx = (size_t)n * L + l;
+        clppd[idx] = clppd[idx] * wgt_old + expf(-nll) * wgt_new;
+        pvy[idx] = pvy[idx] * wgt_old + ((yr_rep <= u.o.yr) ? wgt_new : 0.f);
+    }
+    pvl[n] = pvl[n] * wgt_old + ((nll_rep_sum >= nll_sum) ? wgt_new : 0.f);
+}
+
 // ---- reductions -----------------------------------------------------------------------------
 // out[0] = sum nll, out[1..D] spatial per dim (global convention, factor 1/2), out[1+D..2D] indicator per dim
 __global__ void objective_terms_kernel(PriorDev pr, int N, int D, int max_degree, const float* __restrict__ theta,

@@ -266,6 +266,22 @@ class DevicePosterior:
                                               L.dptr(ua, C.c_float)), "bt_debug_philox_mtm")
         return cand, us, ua
 
+    # ------------------------------------------------------------------ online model checking
+    def model_check_reset(self):
+        L.check(self._lib.bt_model_check_reset(self._ctx), "bt_model_check_reset")
+
+    def model_check_update(self, seed, t, za=None, zm=None):
+        """MySampler._update_model_check_values, sampling branch (sampler/my_sampler.py:158-214)."""
+        za, zm = L.as_f32(za), L.as_f32(zm)
+        L.check(self._lib.bt_model_check_update(self._ctx, seed, t, L.dptr(za, C.c_float), L.dptr(zm, C.c_float)),
+                "bt_model_check_update")
+
+    def model_check_get(self, finalize=True):
+        clppd, pvy, pvl = np.empty((self.N, self.L)), np.empty((self.N, self.L)), np.empty(self.N)
+        L.check(self._lib.bt_model_check_get(self._ctx, L.dptr(clppd), L.dptr(pvy), L.dptr(pvl), int(finalize)),
+                "bt_model_check_get")
+        return clppd, pvy, pvl
+
     def synchronize(self):
         L.check(self._lib.bt_synchronize(self._ctx), "bt_synchronize")
 

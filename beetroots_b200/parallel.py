@@ -252,6 +252,15 @@ class ShardedDevicePosterior:
         a, lp = self.local.step_stats()
         return self._gather_owned(a), self._gather_owned(lp)
 
+    def model_check_reset(self):
+        self.local.model_check_reset()
+
+    def model_check_update(self, seed, t, za=None, zm=None):
+        self.local.model_check_update(seed, t, za, zm)
+
+    def model_check_get(self, finalize=True):
+        return tuple(self._gather_owned(a) for a in self.local.model_check_get(finalize))
+
     def synchronize(self):
         self.local.synchronize()
 

@@ -181,9 +181,7 @@ class B200Sampler:
         assert np.sum(np.isnan(self.v)) == 0.0
         assert np.sum(np.isinf(self.v)) == 0.0
         self.j_t = np.zeros((self.N * self.D,))
-        clppd = np.zeros((self.N, self.L))
-        p_values_y = np.zeros((self.N, self.L))
-        p_values_llh = np.zeros((self.N,))
+        dev.model_check_reset()                                                    # :385-401
 
         try:
             from tqdm.auto import tqdm
@@ -206,6 +204,8 @@ class B200Sampler:
                 additional_sampling_log["accepted_t"] = accepted_t
                 additional_sampling_log["log_proba_accept_t"] = log_proba_accept_t
                 dict_objective = dev.objective_terms()                             # posterior.py:270-330
+                if t > T_BI:                                                       # :468-476 / :514-521
+                    dev.model_check_update(self.philox_seed, t)
                 kw = dict(Theta=self.current["Theta"], forward_map_evals=self.current["forward_map_evals"],
                           nll_utils=self.current["nll_utils"], dict_objective=dict_objective,
                           additional_sampling_log=additional_sampling_log)
@@ -216,7 +216,7 @@ class B200Sampler:
             if saver.check_need_to_save(t):                                        # :539-541
                 saver.save_to_file()
         self._pull_state(with_current=True)
-        # online model checking (clppd, Bayesian p-values, :158-267) is the next widening row
+        clppd, p_values_y, p_values_llh = dev.model_check_get(finalize=True)       # :544-549
         saver.save_additional(list_arrays=[clppd, p_values_y, p_values_llh],
                               list_names=["clppd", "p-values-y", "p-values-llh"])   # :551-558
         return

@@ -145,6 +145,16 @@ int bt_debug_philox_pmala(bt_ctx* ctx, int site, uint64_t seed, int64_t t, float
 int bt_debug_philox_mtm(bt_ctx* ctx, int site, int K, uint64_t seed, int64_t t, float* cand_out,
                         float* usel_out, float* uacc_out);
 
+/* ---- online model checking (sampler/my_sampler.py:158-267, sampling branch) ---------------------
+ * One update per saved iterate: replicated observation y_rep = max(omega, eps_m f + eps_a)
+ * (likelihoods/approx_censored_add_mult.py:268-280), running means of exp(-nll) (clppd), of
+ * [y_rep <= y] and of [nll(y_rep) >= nll(y)] per pixel.  za / zm: HOST float (N, L) standard normals for
+ * the additive / multiplicative noise, or NULL (Philox).  bt_model_check_get with finalize != 0 folds the
+ * p-values-y onto [0, 0.5] (my_sampler.py:260-265).  Any output pointer may be NULL. */
+int bt_model_check_reset(bt_ctx* ctx);
+int bt_model_check_update(bt_ctx* ctx, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject);
+int bt_model_check_get(bt_ctx* ctx, double* clppd, double* pval_y, double* pval_llh, int finalize);
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t bt_kernel_launches(bt_ctx* ctx);
 /* device time (ms) spent in the forward-map kernel since the last call with reset != 0 and the

@@ -82,7 +82,9 @@ def likelihood_eval(lik, fm_evals: dict, idx=None, compute_derivatives: bool = T
     y, omega = lik.y[rows], lik.omega[rows]
     log_fm1, log_fp1 = lik.log_fm1[rows], lik.log_fp1[rows]
     with np.errstate(all="ignore"):
-        log_y = np.log(y)
+        # :999-1000 full maps use the stored self.log_y (which the model check leaves stale, my_sampler.py:176-177);
+        # :1036 candidate rows recompute it
+        log_y = lik.log_y[rows] if idx is None else np.log(y)
         censored_mask = y <= omega                                              # :1042
         sigma_m2 = sigma_m ** 2
         log_combination = np.log(sigma_a) - lf - sigma_m2 / 2                   # :1047-1049

@@ -42,6 +42,37 @@ class OracleSampler:
     def sites(self):
         return list(self.post.dict_sites.keys())
 
+    # ------------------------------------------------------------------ model checking :158-214, :260-265
+    def model_check_reset(self):
+        N, L = self.N, self.post.L
+        self.mc = {"clppd": np.zeros((N, L)), "p_values_y": np.zeros((N, L)), "p_values_llh": np.zeros(N), "count": 0}
+
+    def model_check_update(self, za, zm, y_rep=None):
+        """_update_model_check_values, sampling branch, with the replicated observation of
+        MixingModelsLikelihood.sample_observation_model (approx_censored_add_mult.py:268-280) driven by the
+        standard normals za (additive) and zm (multiplicative)."""
+        import copy
+        lik = self.post.likelihood
+        fm = self.current["forward_map_evals"]
+        nll_full = self.current["nll_full"]
+        c = self.mc["count"]
+        self.mc["clppd"] = self.mc["clppd"] * (c / (c + 1)) + np.exp(-nll_full) / (c + 1)              # :169-170
+        eps_a = lik.sigma_a * za                                                                        # rng.normal(0, sigma_a)
+        eps_m = np.exp(-(lik.sigma_m ** 2) / 2 + lik.sigma_m * zm)                                      # rng.lognormal
+        if y_rep is None:
+            y_rep = np.maximum(lik.omega, eps_m * fm["f_Theta"] + eps_a)                                # :279
+        lik_rep = copy.copy(lik)
+        lik_rep.y = y_rep            # NB the reference does NOT refresh log_y (:176-177): the multiplicative branch of
+        #                              the replicated likelihood keeps ln(y) of the ORIGINAL observation -- reproduced
+        nll_rep = P.likelihood_eval(lik_rep, fm, None, False)["nll_full"]                               # :181-191
+        self.mc["p_values_y"] = self.mc["p_values_y"] * (c / (c + 1)) + (y_rep <= lik.y) / (c + 1)      # :194-195
+        self.mc["p_values_llh"] = self.mc["p_values_llh"] * (c / (c + 1)) + (nll_rep.sum(1) >= nll_full.sum(1)) / (c + 1)
+        self.mc["count"] = c + 1
+
+    def model_check_get(self):
+        py = self.mc["p_values_y"]
+        return self.mc["clppd"], np.where(py > 0.5, 1 - py, py), self.mc["p_values_llh"]               # :260-265
+
     # ------------------------------------------------------------------ PMALA :735-906
     def pmala_step(self, noise: dict):
         post = self.post

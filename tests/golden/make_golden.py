@@ -75,6 +75,18 @@ class TapeRNG:
     def multinomial(self, *a, **k):
         return self.rng.multinomial(*a, **k)
 
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        x = self.rng.normal(loc=loc, scale=scale, size=size)
+        self.log.append(("normal", (np.asarray(x) - loc) / scale))          # the underlying standard normals
+        self.log.append(("normal_raw", np.asarray(x).copy()))
+        return x
+
+    def lognormal(self, mean=0.0, sigma=1.0, size=None):
+        x = self.rng.lognormal(mean=mean, sigma=sigma, size=size)
+        self.log.append(("lognormal", (np.log(np.asarray(x)) - mean) / sigma))
+        self.log.append(("lognormal_raw", np.asarray(x).copy()))
+        return x
+
     def __getattr__(self, name):
         return getattr(self.rng, name)
 
@@ -222,6 +234,33 @@ def run_case(name, H, W, L, K, nnn, seed, censor_boost, drop=(), kernels=(0, 1, 
         out[f"t{t}_grad"] = smp.current["grad"].copy()
         out[f"t{t}_obj_chrom"] = smp.current["objective_pix_chromatic"].copy()
         print(f"[{name}] t={t} kind={'PMALA' if kind else 'MTM'} accept={acc.mean():.3f} OK (oracle == reference)")
+    # --- online model checking (my_sampler.py:158-214): two updates at the final state, replication noise taped
+    dmc = {"clppd_online": np.zeros((N, L)), "best_objective": np.inf, "count_pval": 0,
+           "p_values_y": np.zeros((N, L)), "p_values_llh": np.zeros((N,))}
+    orc.model_check_reset()
+    for r in range(2):
+        tape.log.clear()
+        dobj, nll_full = ref_post.compute_all_for_saver(smp.current["Theta"], smp.current["forward_map_evals"],
+                                                        smp.current["nll_utils"])
+        dmc = smp._update_model_check_values(dmc, ref_post.likelihood, nll_full, dobj["objective"] * 1)
+        za = [e[1] for e in tape.log if e[0] == "normal"][0]
+        zm = [e[1] for e in tape.log if e[0] == "lognormal"][0]
+        out[f"mc{r}_za"], out[f"mc{r}_zm"] = za, zm
+        ea = [e[1] for e in tape.log if e[0] == "normal_raw"][0]
+        em = [e[1] for e in tape.log if e[0] == "lognormal_raw"][0]
+        # exact replicated observation of the reference (za / zm reproduce it only up to one ulp)
+        y_rep = np.maximum(ref_post.likelihood.omega, em * smp.current["forward_map_evals"]["f_Theta"] + ea)
+        orc.model_check_update(za, zm, y_rep=y_rep)
+    fin = smp._finalize_model_check_values(dict(dmc), ref_post.likelihood, smp.current["forward_map_evals"], nll_full)
+    o_c, o_py, o_pl = orc.model_check_get()
+    cmp(fin["clppd_online"], o_c, "clppd", 1e-9)
+    print("   pval_y mismatches", np.sum(fin["p_values_y"] != o_py), "pval_llh mismatches", np.sum(fin["p_values_llh"] != o_pl),
+          "count", dmc["count_pval"], orc.mc["count"])
+    assert np.array_equal(fin["p_values_y"], o_py) and np.array_equal(fin["p_values_llh"], o_pl), "model-check p-values"
+    out["mc_clppd"], out["mc_pval_y"], out["mc_pval_llh"] = fin["clppd_online"], fin["p_values_y"], fin["p_values_llh"]
+    out["mc_dict_objective"] = np.array([dobj["nll"], dobj["objective"]])
+    out["mc_nl_prior_spatial"], out["mc_nl_prior_indicator"] = dobj["nl_prior_spatial"], dobj["nl_prior_indicator"]
+    print(f"[{name}] model check (2 updates) OK (oracle == reference)")
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 

@@ -424,3 +424,64 @@ def test_tensor_core_variants_agree(lib):
             outs.append(dict(np.load(path)))
     assert np.array_equal(outs[0]["lf"], outs[1]["lf"])
     assert np.array_equal(outs[0]["jac"], outs[1]["jac"])
+
+
+def test_model_check_vs_oracle(lib):
+    """Online model checking (clppd, Bayesian p-values; my_sampler.py:158-267) with injected replication noise."""
+    from beetroots_b200 import DevicePosterior
+    from beetroots_b200 import modelling as M
+    from oracle.sampler import OracleSampler
+    prob = _synthetic(9, 7, 5, boost=3.0)
+    post = prob.posterior
+    N, L = post.N, post.L
+    dev = DevicePosterior.from_posterior(post)
+    dev.compute_all(prob.theta_init)
+    nbr = M.build_neighbor_table(post.prior_spatial.list_edges, N, 4)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, 5)
+    orc.init(prob.theta_init)
+    dev.model_check_reset()
+    orc.model_check_reset()
+    rng = np.random.default_rng(11)
+    for t in range(1, 6):
+        za = rng.standard_normal((N, L)).astype(np.float32)
+        zm = rng.standard_normal((N, L)).astype(np.float32)
+        dev.model_check_update(0, t, za, zm)
+        orc.model_check_update(za.astype(np.float64), zm.astype(np.float64))
+    c_g, py_g, pl_g = dev.model_check_get(finalize=True)
+    c_o, py_o, pl_o = orc.model_check_get()
+    assert np.allclose(c_g, c_o, rtol=2e-4, atol=1e-30 + 1e-6 * np.abs(c_o).max())
+    # indicator means: identical up to ties of y_rep vs y / nll_rep vs nll at float32 resolution
+    assert np.mean(np.abs(py_g - py_o) > 1e-6) < 0.01
+    assert np.mean(np.abs(pl_g - pl_o) > 1e-6) < 0.02
+    # Philox path runs and stays in range
+    dev.model_check_reset()
+    for t in range(1, 4):
+        dev.model_check_update(123, t)
+    c, py, pl = dev.model_check_get(finalize=True)
+    assert np.all(np.isfinite(c)) and py.min() >= 0 and py.max() <= 0.5 and pl.min() >= 0 and pl.max() <= 1
+    dev.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_saver_terms_and_model_check_vs_reference_golden(lib, name):
+    """dict_objective of compute_all_for_saver (posterior.py:270-330) and the online model check
+    (my_sampler.py:158-267) at the final golden state, against values recorded from the reference."""
+    from beetroots_b200 import DevicePosterior
+    g = load_golden(name)
+    post, _ = problem_from_golden(g)
+    dev = DevicePosterior.from_posterior(post)
+    T = len(g["kernels"])
+    dev.compute_all(g[f"t{T}_Theta"])
+    terms = dev.objective_terms()
+    assert np.isclose(terms["nll"], g["mc_dict_objective"][0], rtol=2e-6)
+    assert np.isclose(terms["objective"], g["mc_dict_objective"][1], rtol=2e-6)
+    assert np.allclose(terms["nl_prior_spatial"], g["mc_nl_prior_spatial"], rtol=1e-5)
+    assert np.allclose(terms["nl_prior_indicator"], g["mc_nl_prior_indicator"], rtol=1e-5, atol=1e-12)
+    dev.model_check_reset()
+    for r in range(2):
+        dev.model_check_update(0, r + 1, g[f"mc{r}_za"], g[f"mc{r}_zm"])
+    c, py, pl = dev.model_check_get(finalize=True)
+    assert np.allclose(c, g["mc_clppd"], rtol=5e-4, atol=1e-6 * np.abs(g["mc_clppd"]).max())
+    assert np.mean(np.abs(py - g["mc_pval_y"]) > 1e-6) < 0.02
+    assert np.mean(np.abs(pl - g["mc_pval_llh"]) > 1e-6) < 0.08
+    dev.close()

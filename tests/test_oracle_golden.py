@@ -104,3 +104,19 @@ def test_mills_ratio():
     x = np.linspace(-30, 10, 200)
     r = OP._norm_pdf_cdf_ratio(x)
     assert np.all(np.diff(r) < 0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_model_check_matches_reference(name):
+    """clppd / Bayesian p-values after two updates at the final golden state (my_sampler.py:158-267)."""
+    g = load_golden(name)
+    post, nbr = problem_from_golden(g)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, int(g["K"]))
+    T = len(g["kernels"])
+    orc.init(g[f"t{T}_Theta"])
+    orc.model_check_reset()
+    for r in range(2):
+        orc.model_check_update(g[f"mc{r}_za"], g[f"mc{r}_zm"])
+    c, py, pl = orc.model_check_get()
+    assert rel(c, g["mc_clppd"]) < 1e-8
+    assert np.mean(py != g["mc_pval_y"]) < 0.01 and np.mean(pl != g["mc_pval_llh"]) < 0.05   # za/zm reproduce y_rep to 1 ulp
