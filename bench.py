@@ -167,7 +167,7 @@ def run_ours(args):
     K = args.k_mtm
     mode = {"fp32": MLP_FP32, "bf16": MLP_BF16_TC}.get(args.mlp)
     if mode is None:
-        mode = MLP_BF16_TC if os.environ.get("BT_BENCH_BF16", "1") == "1" else MLP_FP32
+        mode = MLP_BF16_TC
     prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K)
     post = prob.posterior
     try:

@@ -485,3 +485,34 @@ def test_saver_terms_and_model_check_vs_reference_golden(lib, name):
     assert np.mean(np.abs(py - g["mc_pval_y"]) > 1e-6) < 0.02
     assert np.mean(np.abs(pl - g["mc_pval_llh"]) > 1e-6) < 0.08
     dev.close()
+
+
+def test_error_behaviour_through_the_abi(lib):
+    """Reference error conventions that survive at the boundary."""
+    from beetroots_b200 import MLP_BF16_TC, DevicePosterior
+    from beetroots_b200 import modelling as M
+    from beetroots_b200._lib import BeetrootsB200Error
+    prob = _synthetic(6, 6, 4)
+    post = prob.posterior
+    dev = DevicePosterior.from_posterior(post)
+    bad = prob.theta_init.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises((AssertionError, BeetrootsB200Error)):        # posterior.py:360
+        dev.compute_all(bad)
+    with pytest.raises(BeetrootsB200Error):
+        dev.pmala_site(7, 1e-4, 1e-5, 0.99, 1, 1)                    # no such colour class
+    dev.close()
+    # MTM needs the smooth indicator prior (my_sampler.py:132-133 raises ValueError)
+    post2 = M.Posterior(post.D, post.L, post.N, post.likelihood, post.prior_spatial, None)
+    dev2 = DevicePosterior.from_posterior(post2)
+    dev2.compute_all(prob.theta_init)
+    with pytest.raises(BeetrootsB200Error, match="indicator"):
+        dev2.mtm_site(0, 4, 1, 1)
+    dev2.close()
+    # tensor-core mode refuses networks it cannot hold (more than 32 output lines) instead of silently falling back
+    from beetroots_b200.network import synthetic_weights
+    net = synthetic_weights(0, 40)
+    fm = M.NeuralNetworkApprox(net, {"kappa": None, "P": None, "radm": None, "Avmax": None, "angle": 0.0})
+    lik = M.MixingModelsLikelihood(fm, 4, 40, 4, np.ones((4, 40)), 1.0, 0.1, 0.5, a0=np.zeros((1, 40)), a1=np.ones((1, 40)))
+    with pytest.raises(BeetrootsB200Error, match="tensor-core"):
+        DevicePosterior.from_posterior(M.Posterior(4, 40, 4, lik, None, None), mlp_mode=MLP_BF16_TC)
