@@ -56,6 +56,38 @@ def _network_weights(network) -> DenseMLPWeights:
     return net
 
 
+def host_inputs_from_posterior(posterior, dict_sites=None) -> dict:
+    """Everything the device needs, read from a (reference or mirror) ``Posterior`` by attribute name -- pure host
+    code, no CUDA.  This is the drop-in boundary: tests/test_reference_dropin.py runs it on UNMODIFIED reference
+    objects (build container) and on the mirrors and checks that both give the same arrays."""
+    lik = posterior.likelihood
+    fm = lik.forward_map
+    N, D, Lines = int(posterior.N), int(posterior.D), int(posterior.L)
+    ps, pi = posterior.prior_spatial, posterior.prior_indicator
+    if ps is not None:
+        nnn = bool(getattr(ps, "use_next_nearest_neighbors", True))
+        max_degree = 8 if nnn else 4
+        nbr = build_neighbor_table(ps.list_edges, N, max_degree)
+    else:
+        max_degree, nbr = 1, -np.ones((N, 1), dtype=np.int32)
+    net = _network_weights(fm.network)
+    assert net.n_out == Lines, "restrict the network to the fitted lines first"
+    obs = {k: L.as_f64(np.broadcast_to(np.asarray(getattr(lik, k), dtype=np.float64), (N, Lines)))
+           for k in ("y", "sigma_a", "sigma_m", "omega", "log_fm1", "log_fp1")}
+    sites = dict_sites if dict_sites is not None else posterior.dict_sites
+    return {
+        "N": N, "D": D, "L": Lines, "max_degree": max_degree, "nbr": L.as_i32(nbr), "net": net,
+        "fixed": L.as_f64(fm.arr_fixed_values),
+        "sampled_idx": L.as_i32(np.array(fm.list_indices_to_sample, dtype=np.int32)),
+        "obs": obs,
+        "site_keys": list(sites.keys()),
+        "site_pixels": [L.as_i32(np.asarray(sites[k])) for k in sites.keys()],
+        "tau": None if ps is None else L.as_f64(ps.weights), "tau_init": None if ps is None else L.as_f64(ps.initial_weights),
+        "lower": None if pi is None else L.as_f64(pi.lower_bounds), "upper": None if pi is None else L.as_f64(pi.upper_bounds),
+        "delta": None if pi is None else float(pi.indicator_margin_scale),
+    }
+
+
 class DevicePosterior:
     def __init__(self, ctx, N, D, n_lines, n_sites, site_keys, site_pixels, max_degree):
         self._ctx = ctx
@@ -72,24 +104,16 @@ class DevicePosterior:
                        dict_sites: Optional[Dict[int, np.ndarray]] = None, mlp_mode: int = MLP_FP32,
                        stream: int = 0) -> "DevicePosterior":
         lib = L.load()
-        lik = posterior.likelihood
-        fm = lik.forward_map
-        N, D, Lines = int(posterior.N), int(posterior.D), int(posterior.L)
+        hi = host_inputs_from_posterior(posterior, dict_sites)
+        N, D, Lines, max_degree, nbr = hi["N"], hi["D"], hi["L"], hi["max_degree"], hi["nbr"]
         ps, pi = posterior.prior_spatial, posterior.prior_indicator
-        if ps is not None:
-            nnn = bool(getattr(ps, "use_next_nearest_neighbors", True))
-            max_degree = 8 if nnn else 4
-            nbr = build_neighbor_table(ps.list_edges, N, max_degree)
-        else:
-            max_degree, nbr = 1, -np.ones((N, 1), dtype=np.int32)
         ctx = C.c_void_p()
         L.check(lib.bt_ctx_create(C.byref(ctx), device, N, D, Lines, max_degree), "bt_ctx_create")
         self = cls(ctx, N, D, Lines, 0, [], [], max_degree)
         try:
             if stream:
                 L.check(lib.bt_set_stream(ctx, stream), "bt_set_stream")
-            net = _network_weights(fm.network)
-            assert net.n_out == Lines, "restrict the network to the fitted lines first"
+            net = hi["net"]
             nb = len(net.weights)
             Ws = [L.as_f64(w) for w in net.weights]
             Bs = [L.as_f64(b) for b in net.biases]
@@ -102,17 +126,14 @@ class DevicePosterior:
             L.check(lib.bt_upload_network(ctx, net.n_in, net.order, net.n_feat0, L.dptr(exps, C.c_int32), L.dptr(means),
                                           L.dptr(stds), nb, L.dptr(bnew, C.c_int32), WP, BP, L.dptr(w_out),
                                           L.dptr(b_out), net.n_out), "bt_upload_network")
-            fixed = L.as_f64(fm.arr_fixed_values)
-            idx = L.as_i32(np.array(fm.list_indices_to_sample, dtype=np.int32))
+            fixed, idx = hi["fixed"], hi["sampled_idx"]
             L.check(lib.bt_upload_forward_map(ctx, fixed.size, L.dptr(fixed), idx.size, L.dptr(idx, C.c_int32)),
                     "bt_upload_forward_map")
-            arrs = [L.as_f64(np.broadcast_to(np.asarray(getattr(lik, k), dtype=np.float64), (N, Lines)))
-                    for k in ("y", "sigma_a", "sigma_m", "omega", "log_fm1", "log_fp1")]
+            arrs = [hi["obs"][k] for k in ("y", "sigma_a", "sigma_m", "omega", "log_fm1", "log_fp1")]
             L.check(lib.bt_upload_observations(ctx, *[L.dptr(a) for a in arrs]), "bt_upload_observations")
             self._upload_priors(ps, pi)
-            sites = dict_sites if dict_sites is not None else posterior.dict_sites
-            self.site_keys = list(sites.keys())
-            self.site_pixels = [L.as_i32(np.asarray(sites[k])) for k in self.site_keys]
+            self.site_keys = hi["site_keys"]
+            self.site_pixels = hi["site_pixels"]
             self.n_sites = len(self.site_keys)
             sizes = L.as_i32(np.array([p.size for p in self.site_pixels], dtype=np.int32))
             pix = L.as_i32(np.concatenate(self.site_pixels)) if self.n_sites else np.zeros(0, np.int32)

@@ -60,6 +60,25 @@ class NeuralNetwork(torch.nn.Module):
         rows = torch.as_tensor(self._rows, dtype=torch.long)
         return torch.nn.functional.linear(h, self.W_out_full[rows], self.b_out_full[rows])
 
+    def state_dict(self, *a, **k):
+        """Key names of a real nnbma PolynomialNetwork -> DenselyConnected checkpoint (data/models/*/parameters.pth,
+        state_dict.pth), so beetroots_b200.device._network_weights can be exercised on it."""
+        sd = {"poly.means": self.means, "poly.stds": self.stds}
+        for i, (W, b) in enumerate(zip(self.Ws, self.bs)):
+            sd[f"subnetwork.layers.{i}.weight"], sd[f"subnetwork.layers.{i}.bias"] = W, b
+        sd["subnetwork.output_layer.weight"], sd["subnetwork.output_layer.bias"] = self.W_out_full, self.b_out_full
+        return sd
+
+    @property
+    def subnetwork(self):
+        class _Sub:
+            pass
+        sub = _Sub()
+        sub.current_output_subset_indices = list(self._rows)
+        return sub
+
+    order = 3
+
     def evaluate(self, x: np.ndarray) -> np.ndarray:
         with torch.no_grad():
             return self.forward(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))).numpy()
