@@ -13,6 +13,7 @@
 #include "sampler_kernels.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
+#include "mlp_tc3.cuh"
 
 static thread_local std::string g_err;
 static int fail(const char* what, const char* file, int line, cudaError_t e = cudaSuccess) {
@@ -39,6 +40,7 @@ struct bt_ctx {
     std::vector<void*> net_allocs;
     std::vector<double> shift;          // per-line output bias (natural log), added back on the host side
     TcNet tc{};                         // bf16 tensor-core copy of the weights (mlp_tc.cuh)
+    Tc3Net tc3{};                       // pair kernel, third generation (mlp_tc3.cuh)
     Tc2Net tc2{};                       // same for the cta_group::2 kernel (mlp_tc2.cuh)
     // data
     ObsConst* obs = nullptr;
@@ -137,6 +139,7 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
     for (void* p : c->net_allocs) cudaFree(p);
     tc_free(c->tc);
     tc2_free(c->tc2);
+    tc3_free(c->tc3);
     void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
                     c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl};
@@ -219,6 +222,8 @@ extern "C" int bt_upload_network(bt_ctx* c, int n_in, int order, int n_feat0, co
     tc_build(c->tc, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, LOGE10);
     tc2_free(c->tc2);
     tc2_build(c->tc2, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, LOGE10);
+    tc3_free(c->tc3);
+    tc3_build(c->tc3, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, LOGE10);
     return 0;
 }
 
@@ -388,7 +393,8 @@ static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
     }
     if (c->mlp_mode == BT_MLP_BF16_TC) {
         static const int variant = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 1;   // 1 = single-CTA kernel (fastest so far), 2 = cta_group::2
-        int rc = (variant == 2 && c->tc2.ready) ? tc2_launch(c->tc2, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
+        int rc = (variant == 3 && c->tc3.ready) ? tc3_launch(c->tc3, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
+               : (variant == 2 && c->tc2.ready) ? tc2_launch(c->tc2, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
                                                 : tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);
         if (rc) return fail("tensor-core MLP launch failed", __FILE__, __LINE__);
         KLAUNCH(c);

@@ -362,6 +362,7 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
 #pragma unroll
                     for (int r = 0; r < 8; ++r) swz[r] = dst + (uint32_t)(r * 128) + ((chunk ^ (uint32_t)r) << 4);
 #pragma unroll
+                    const int fine = (rec && mt == 0 && (l == 0 || l == 8)) ? 100 + (l ? 8 : 0) : -1;
                     for (int half = 0; half < 2; ++half) {                   // my 64 columns = two 32-column TMEM loads
                         float v[32];
                         const uint32_t tcol = (uint32_t)(h * 64 + half * 32);
@@ -372,6 +373,7 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += w[j];
                         }
+                        if (fine >= 0) sch.dbg[fine + 2 * half] = clock64();
                         if (half == 1) {                                     // both halves read: the slots can be refilled
                             tc_fence_before();
                             __syncwarp();
@@ -407,14 +409,17 @@ mlp_tc2_kernel(Tc2Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                                 }
                             }
                         }
+                        if (fine >= 0) sch.dbg[fine + 2 * half + 1] = clock64();
                     }
                     if (!L.is_out) {
                         // .shared::cluster / unqualified forms lower to MEMBAR.ALL.GPU, which stalls the whole SM for
                         // thousands of cycles; the CTA-scoped form orders this thread's generic stores (local and
                         // DSMEM) before the async-proxy reads that follow the barrier hand-off
                         fence_proxy_async();
+                        if (fine >= 0) sch.dbg[fine + 4] = clock64();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(l_lready + 8 * (l + 1));
+                        if (fine >= 0) sch.dbg[fine + 5] = clock64();
                         if (rec && mt == L.n_mt - 1) sch.dbg[69 + 3 * l] = clock64();
                     }
                 }
@@ -471,6 +476,12 @@ static inline int tc2_launch(Tc2Net& t, const FmapDev& fm, const NetDev& net, co
                 h[64] - t0, h[65] - t0, h[66] - t0);
         for (int l = 0; l < t.sched.n_layers; ++l)
             fprintf(stderr, "L%d wait %lld..%lld done %lld | ", l, h[67 + 3 * l] - t0, h[68 + 3 * l] - t0, h[69 + 3 * l] - t0);
+        fprintf(stderr, "\n[tc2 fine] ");
+        for (int i = 0; i < 2; ++i) {
+            const long long w0 = h[68 + 3 * (i ? 8 : 0)];
+            fprintf(stderr, "L%d: ld0 %lld st0 %lld ld1 %lld st1 %lld fence %lld arrive %lld | ", i ? 8 : 0, h[100 + 8 * i] - w0,
+                    h[101 + 8 * i] - w0, h[102 + 8 * i] - w0, h[103 + 8 * i] - w0, h[104 + 8 * i] - w0, h[105 + 8 * i] - w0);
+        }
         fprintf(stderr, "\n");
     }
     return 0;

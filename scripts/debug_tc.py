@@ -24,3 +24,8 @@ if jac:
     dj = out["grad_log_f_Theta"] - ref["grad_log_f_Theta"]
     print("max |d jac|", np.abs(dj).max(), "jac scale", np.abs(ref["grad_log_f_Theta"]).max())
     print(out["grad_log_f_Theta"][0, :, 0], ref["grad_log_f_Theta"][0, :, 0])
+if os.environ.get("BT_DBG_ROWS"):
+    e = np.abs(d).max(axis=1)
+    n = min(Mrows, 256)
+    print("per-row max err, blocks of 16 rows:", [float(f"{e[i:i+16].max():.3f}") for i in range(0, n, 16)])
+    print("per-line max err:", [float(f"{x:.3f}") for x in np.abs(d).max(axis=0)])
