@@ -392,7 +392,7 @@ static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
         CK(cudaEventRecord(e0, c->stream));
     }
     if (c->mlp_mode == BT_MLP_BF16_TC) {
-        static const int variant = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 1;   // 1 = single-CTA kernel (fastest so far), 2 = cta_group::2
+        static const int variant = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 3;   // 3 = pair kernel (mlp_tc3.cuh, default), 1 = single-CTA kernel, 2 = first cta_group::2 kernel
         int rc = (variant == 3 && c->tc3.ready) ? tc3_launch(c->tc3, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
                : (variant == 2 && c->tc2.ready) ? tc2_launch(c->tc2, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
                                                 : tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);

@@ -24,6 +24,7 @@
 #define TC3_MAX_UNITS 24
 #define TC3_F_CONT 1               // accumulate onto the previous unit's slots (no wait for "empty", first MMA accumulates)
 #define TC3_F_HOLD 2               // the epilogue leaves the slots allocated: a CONT unit follows
+#define TC3_F_PUB 8                // after this unit's accumulators complete nothing of this tile reads K-block 0 any more: publish the next tile's inputs
 #define TC3_F_FINAL 4              // lanes [0, n_out) of CTA 0 hold the finished output layer
 #define TC3_MISC_BYTES 4096
 
@@ -32,6 +33,7 @@ struct Tc3Unit {
     short new_k16;                 // first step holding features guarded by ready barrier `dep`
     short dep, sp, flags, ready_idx, two;
     int ring_lo;                   // chunks of this unit may live in [ring_lo, ring_bytes) of the extended ring
+    short cw;                      // K-blocks per weight chunk (handshake granularity): 1 or 2
     short rep;                     // small units: the rows are replicated in rep lane groups, each handles 32/rep of a warp's columns
     short groups[2];               // 8-row groups of weights streamed per K-block, per CTA
     short gelu_lane0[2], gelu_rows[2];
@@ -122,7 +124,7 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
             if (U.groups[0] > 16 || U.groups[1] > 16) return 0;
             U.feat0[0] = in + 256 * mt;
             U.feat0[1] = in + 256 * mt + U.gelu_rows[0];
-            s.ready_count[l + 1] += 2;
+            s.ready_count[l + 1] += (U.gelu_rows[0] > 0) + (U.gelu_rows[1] > 0);   // one arrival per CTA that produces features
             for (int c = 0; c < 2; ++c) {
                 std::vector<RowSrc> rs((size_t)U.groups[c] * 8, RowSrc{-2, 0, 0, 0});
                 if (c == 0 && fold) for (int r = 0; r < n_out; ++r) rs[r] = RowSrc{-1, r, 0, in};
@@ -162,7 +164,32 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
         }
         ++nu;
     }
+    {
+        int last0 = 0;
+        for (int u = 0; u < nu; ++u) if (s.U[u].k16_begin < 4) last0 = u;   // reads K-block 0
+        s.U[last0].flags |= TC3_F_PUB;
+    }
     s.n_units = nu;
+    // Handshake granularity: every weight chunk costs the single-thread pipeline roles (producer, relay, helper, issuer) a fixed
+    // few hundred cycles whatever its size (the bare synchronisation skeleton is ~70 % of the kernel time), so units with many
+    // K-blocks stream two K-blocks per chunk.  Both CTAs then stream the same number of 8-row groups (zero rows pad the
+    // smaller half) so that the second K-block sits at the same offset in both.
+    {
+        static const int cw_env = getenv("BT_TC3_CW") ? atoi(getenv("BT_TC3_CW")) : 2;
+        for (int u = 0; u < nu; ++u) {
+            Tc3Unit& U = s.U[u];
+            const int nkb = (U.k16_end + 3) / 4 - U.k16_begin / 4;
+            U.cw = (short)((cw_env >= 2 && nkb >= 4) ? 2 : 1);
+            if (!(U.flags & TC3_F_CONT) && !(U.flags & TC3_F_FINAL)) U.two = (short)((nkb + U.cw - 1) / U.cw >= 2);
+            if (U.cw == 2) {
+                const short g = std::max(U.groups[0], U.groups[1]);
+                for (int c = 0; c < 2; ++c) {
+                    U.groups[c] = g;
+                    rows_of[c][u].resize((size_t)g * 8, RowSrc{-2, 0, 0, 0});
+                }
+            }
+        }
+    }
     s.act_kb = (n_feat + TC_BK - 1) / TC_BK;
     const long ring = 227L * 1024 - 1024 - (long)s.act_kb * TC_KB_BYTES - TC3_MISC_BYTES;
     if (ring < 32 * 1024) return 0;
@@ -315,13 +342,26 @@ __device__ __forceinline__ void tc3_poly_feats(const int* pexp_s, const float* p
     }
 }
 
+__device__ __forceinline__ void umma2_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_f(uint32_t bar, uint32_t parity, bool spin) {
     if (spin) mbar_spin(bar, parity); else mbar_wait(bar, parity);
 }
-template <int S>
+template <int S, int DBG>   // DBG: 0 = production, 1 = runtime debug flags / timelines, > 1 = these knock-out flags compiled in
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ rows, int M, float* __restrict__ lf,
                float* __restrict__ jac) {
+    // debug knobs / timeline buffers compile away in the production instantiation
+    const int dbg_flags = DBG == 1 ? sch.dbg_flags : DBG;
+    long long* const dbg_buf = DBG == 1 ? sch.dbg : nullptr;
+    long long* const trace_buf = DBG == 1 ? sch.trace : nullptr;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* act = smem;                                             // [act_kb][64 columns x 64 features bf16, SW128]
@@ -347,7 +387,8 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
     const uint32_t ring_bytes = (uint32_t)sch.ring_bytes;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3 * TC3_NT; ++i) mbar_init(bar_full + 8 * i, 1);
+        // leader: a chunk is "full" when its own rows have landed (producer's expect_tx arrival + bytes) AND the peer's relay has arrived
+        for (int i = 0; i < 3 * TC3_NT; ++i) mbar_init(bar_full + 8 * i, (i < TC3_NT && crank == 0) ? 2 : 1);
         for (int i = 0; i < 4; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 2); }
         for (int l = 0; l < sch.n_ready; ++l) mbar_init(bar_lready + 8 * l, sch.ready_count[l]);
         *reinterpret_cast<volatile uint32_t*>(misc + 1004) = 0u;
@@ -390,12 +431,16 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
             for (int pt = pt0; pt < n_ptiles; pt += pt_step)
                 for (int u = 0; u < sch.n_units; ++u) {
                     const Tc3Unit U = sch.U[u];
-                    const uint32_t adv = (sch.dbg_flags & 1) ? 16384u : (uint32_t)(U.groups[0] > U.groups[1] ? U.groups[0] : U.groups[1]) * 1024u;
-                    const uint32_t bytes = (uint32_t)U.groups[crank] * 1024u;
+                    const uint32_t adv_kb = (dbg_flags & 1) ? 16384u : (uint32_t)(U.groups[0] > U.groups[1] ? U.groups[0] : U.groups[1]) * 1024u;
+                    const uint32_t bytes_kb = (uint32_t)U.groups[crank] * 1024u;
                     const uint8_t* src = sch.wstream[crank] + (size_t)U.w_off[crank] * 1024;
-                    for (int kb = U.k16_begin >> 2; kb < (U.k16_end + 3) >> 2; ++kb, ++i, src += bytes) {
-                        // a 128-row operand window (16 KB) must end inside the ring; chunks of this unit start at >= ring_lo
-                        if (pos + 16384u > ring_bytes) { vpos += ring_bytes - pos; pos = 0; }
+                    const int kb1 = (U.k16_end + 3) >> 2;
+                    const uint32_t win = (uint32_t)U.cw * 16384u;
+                    for (int kb = U.k16_begin >> 2; kb < kb1; kb += U.cw, ++i) {
+                        const uint32_t nk = (uint32_t)(kb1 - kb < U.cw ? kb1 - kb : U.cw);
+                        const uint32_t adv = adv_kb * nk, bytes = bytes_kb * nk;
+                        // the 128-row operand windows (16 KB per K-block) must end inside the ring; chunks of this unit start at >= ring_lo
+                        if (pos + win > ring_bytes) { vpos += ring_bytes - pos; pos = 0; }
                         if (pos < (uint32_t)U.ring_lo) { vpos += (uint32_t)U.ring_lo - pos; pos = (uint32_t)U.ring_lo; }
                         const uint32_t t = i % TC3_NT;
                         if (i % TC3_NPROD != pid) {                          // somebody else's chunk: just remember where it lives
@@ -403,17 +448,18 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                             cst[t] = vpos;
                             pos += adv;
                             vpos += adv;
+                            src += bytes;
                             continue;
                         }
                         const uint32_t lo = vpos + adv - ring_bytes;         // oldest virtual byte that survives this chunk
                         while (tail < i && (tail + TC3_NT <= i || (int32_t)(lo - cst[tail % TC3_NT]) > 0)) {
                             mbar_spin(bar_empty + 8 * (tail % TC3_NT), (tail / TC3_NT) & 1u);
-                            if (sch.trace && blockIdx.x == 0 && tail - (uint32_t)sch.trace_i0 < 128u) sch.trace[640 + tail - sch.trace_i0] = clock64();
+                            if (trace_buf && blockIdx.x == 0 && tail - (uint32_t)sch.trace_i0 < 128u) trace_buf[640 + tail - sch.trace_i0] = clock64();
                             ++tail;
                         }
                         cst[t] = vpos;
-                        if (sch.trace && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u) sch.trace[i - sch.trace_i0] = clock64();
-                        if (bytes && !(sch.dbg_flags & 256)) {
+                        if (trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u) trace_buf[i - sch.trace_i0] = clock64();
+                        if (bytes && !(dbg_flags & 256)) {
                             mbar_expect_tx(bar_full + 8 * t, bytes);
                             bulk_g2s(ring_addr + pos, src, bytes, bar_full + 8 * t);
                         } else {
@@ -421,6 +467,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                         }
                         pos += adv;
                         vpos += adv;
+                        src += bytes;
                     }
                 }
         }
@@ -431,14 +478,12 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
             uint32_t i = 0;
             for (int pt = pt0; pt < n_ptiles; pt += pt_step)
                 for (int u = 0; u < sch.n_units; ++u) {
-                    const int n = ((sch.U[u].k16_end + 3) >> 2) - (sch.U[u].k16_begin >> 2);
+                    const int n = (((sch.U[u].k16_end + 3) >> 2) - (sch.U[u].k16_begin >> 2) + sch.U[u].cw - 1) / sch.U[u].cw;
                     for (int k = 0; k < n; ++k, ++i) {
                         const uint32_t t = i % TC3_NT, ph = (i / TC3_NT) & 1u;
-                        const bool tr = sch.trace && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
+                        const bool tr = trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
                         mbar_spin(bar_full + 8 * t, ph);
-                        if (tr) sch.trace[128 + i - sch.trace_i0] = clock64();
-                        mbar_spin(bar_pfull + 8 * t, ph);
-                        if (tr) sch.trace[256 + i - sch.trace_i0] = clock64();
+                        if (tr) trace_buf[128 + i - sch.trace_i0] = clock64();
                         asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ready_cnt), "r"(i + 1u) : "memory");
                     }
                 }
@@ -446,11 +491,11 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
     } else if (warp == 3) {
         // ===================== relay (peer CTA): "my chunk has landed" -> leader =====================
         if (lane == 0 && crank == 1) {
-            const uint32_t leader_pfull = mapa_u32(bar_pfull, 0);
+            const uint32_t leader_pfull = mapa_u32(bar_full, 0);     // second arrival of the leader's "full" barrier
             uint32_t i = 0;
             for (int pt = pt0; pt < n_ptiles; pt += pt_step)
                 for (int u = 0; u < sch.n_units; ++u) {
-                    const int n = ((sch.U[u].k16_end + 3) >> 2) - (sch.U[u].k16_begin >> 2);
+                    const int n = (((sch.U[u].k16_end + 3) >> 2) - (sch.U[u].k16_begin >> 2) + sch.U[u].cw - 1) / sch.U[u].cw;
                     for (int k = 0; k < n; ++k, ++i) {
                         const uint32_t t = i % TC3_NT;
                         mbar_spin(bar_full + 8 * t, (i / TC3_NT) & 1u);
@@ -464,62 +509,77 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
         if (lane == 0 && crank == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(TC2_BM >> 4) << 24);
             const uint32_t act_addr = smem_u32(act), ring_addr = smem_u32(ring);
-            const uint64_t desc_base = umma_desc_sw128(0);
+            const uint32_t desc_lo0 = 1u << 16, desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // umma_desc_sw128(0), split in words
             uint32_t i = 0, pos = 0, nacq0 = 0, nacq1 = 0, tcount = 0, ready_seen = 0;
             for (int pt = pt0; pt < n_ptiles; pt += pt_step, ++tcount) {
-                const bool rec = sch.dbg && blockIdx.x == 0 && tcount == 1 && par == 0;
-                if (rec) sch.dbg[0] = clock64();
+                const bool rec = dbg_buf && blockIdx.x == 0 && tcount == 1 && par == 0;
+                if (rec) dbg_buf[0] = clock64();
                 for (int u = 0; u < sch.n_units; ++u) {
                     const Tc3Unit U = sch.U[u];
-                    const uint32_t adv = (sch.dbg_flags & 1) ? 16384u : (uint32_t)(U.groups[0] > U.groups[1] ? U.groups[0] : U.groups[1]) * 1024u;
+                    const uint32_t adv = (dbg_flags & 1) ? 16384u : (uint32_t)(U.groups[0] > U.groups[1] ? U.groups[0] : U.groups[1]) * 1024u;   // per K-block
                     const uint32_t slot = 2u * (uint32_t)U.sp + (uint32_t)par;
-                    if (rec) sch.dbg[1 + 2 * u] = clock64();
-                    long long c0 = 0, a_te = 0, a_lr = 0, a_fu = 0, a_pf = 0, a_is = 0;
-                    if (rec) c0 = clock64();
+                    if (rec) dbg_buf[1 + 2 * u] = clock64();
                     uint32_t acc = 1u;
                     if (!(U.flags & TC3_F_CONT)) {
                         const uint32_t k = U.sp ? nacq1++ : nacq0++;
-                        mbar_wait_f(bar_tempty + 8 * slot, (k & 1u) ^ 1u, sch.dbg_flags & 32);
+                        mbar_wait_f(bar_tempty + 8 * slot, (k & 1u) ^ 1u, dbg_flags & 32);
                         tc_fence_after();
                         acc = 0u;
                     }
-                    if (rec) { const long long c1 = clock64(); a_te = c1 - c0; c0 = c1; }
                     const uint32_t d_tmem = tmem_base + slot * TC2_BN;
                     bool waited = false;
-                    for (int kb = U.k16_begin >> 2; kb < (U.k16_end + 3) >> 2; ++kb, ++i) {
-                        if (pos + 16384u > ring_bytes) pos = 0;
-                        if (pos < (uint32_t)U.ring_lo) pos = (uint32_t)U.ring_lo;
+                    const int kb0 = U.k16_begin >> 2, kb1 = (U.k16_end + 3) >> 2, cw = U.cw;
+                    const uint32_t ring_lo = (uint32_t)U.ring_lo, win = (uint32_t)cw * 16384u;
+                    const int k16b = U.k16_begin, k16e = U.k16_end, new_k16 = U.new_k16;
+                    int ci = 0;
+                    for (int kbc = kb0; kbc < kb1; kbc += cw, ++i, ++ci) {
+                        const int nk = kb1 - kbc < cw ? kb1 - kbc : cw;
+                        if (pos + win > ring_bytes) pos = 0;
+                        if (pos < ring_lo) pos = ring_lo;
                         const uint32_t cur = pos;
-                        pos += adv;
-                        if ((sch.dbg_flags & 2) ? par != 0 : (kb & 1) != par) continue;
-                        const int ks_lo = U.k16_begin - 4 * kb > 0 ? U.k16_begin - 4 * kb : 0;
-                        const int ks_hi = U.k16_end - 4 * kb < 4 ? U.k16_end - 4 * kb : 4;
-                        if (rec) c0 = clock64();
-                        if (!waited && 4 * kb + ks_hi > U.new_k16) {
-                            mbar_wait_f(bar_lready + 8 * U.dep, tcount & 1u, sch.dbg_flags & 32);
-                            if (rec) sch.dbg[2 + 2 * u] = clock64();
-                            waited = true;
-                        }
-                        if (rec) { const long long c1 = clock64(); a_lr += c1 - c0; c0 = c1; }
+                        pos += adv * (uint32_t)nk;
+                        if ((dbg_flags & 2) ? par != 0 : (ci & 1) != par) continue;
                         const uint32_t t = i % TC3_NT;
-                        while ((int32_t)(ready_seen - (i + 1u)) < 0)         // weights of chunk i landed in both CTAs?
-                            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ready_seen) : "r"(ready_cnt) : "memory");
-                        if (rec) { const long long c1 = clock64(); a_fu += c1 - c0; c0 = c1; }
-                        const bool tr = sch.trace && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
-                        if (tr) sch.trace[384 + i - sch.trace_i0] = clock64();
-                        const uint64_t a_desc = desc_base + ((ring_addr + cur) >> 4);
-                        const uint64_t b_desc = desc_base + ((act_addr + kb * TC_KB_BYTES) >> 4);
+                        bool polled = false;
+                        for (int q = 0; q < nk; ++q) {
+                            const int kb = kbc + q;
+                            const int ks_lo = kb == kb0 ? (k16b & 3) : 0;
+                            const int ks_hi = kb == kb1 - 1 ? k16e - 4 * kb : 4;
+                            if (!waited && 4 * kb + ks_hi > new_k16) {
+                                mbar_wait_f(bar_lready + 8 * U.dep, tcount & 1u, dbg_flags & 32);
+                                if (rec) dbg_buf[2 + 2 * u] = clock64();
+                                waited = true;
+                            }
+                            if (!polled) {
+                                while ((int32_t)(ready_seen - (i + 1u)) < 0)     // weights of chunk i landed in both CTAs?
+                                    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ready_seen) : "r"(ready_cnt) : "memory");
+                                polled = true;
+                                const bool tr = trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
+                                if (tr) trace_buf[384 + i - sch.trace_i0] = clock64();
+                            }
+                            // descriptors differ only in the 14-bit start-address field of the low word
+                            const uint32_t a_lo = desc_lo0 + ((ring_addr + cur + (uint32_t)q * adv) >> 4);
+                            const uint32_t b_lo = desc_lo0 + ((act_addr + kb * TC_KB_BYTES) >> 4);
+                            if (!(dbg_flags & 8)) {
+                                if (ks_lo == 0 && ks_hi == 4) {
+                                    umma2_f16_lo(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
+                                    umma2_f16_lo(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                    umma2_f16_lo(d_tmem, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                    umma2_f16_lo(d_tmem, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                    acc = 1u;
+                                } else {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            if (ks >= ks_lo && ks < ks_hi && !(sch.dbg_flags & 8)) { umma2_f16(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, acc); acc = 1u; }
+                                    for (int ks = 0; ks < 4; ++ks)
+                                        if (ks >= ks_lo && ks < ks_hi) { umma2_f16_lo(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, acc); acc = 1u; }
+                                }
+                            }
+                        }
                         umma2_commit_mc(bar_empty + 8 * t, 3);              // frees the chunk in both CTAs
-                        if (tr) sch.trace[512 + i - sch.trace_i0] = clock64();
-                        if (rec) { const long long c1 = clock64(); a_is += c1 - c0; c0 = c1; }
+                        if (trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u) trace_buf[512 + i - sch.trace_i0] = clock64();
                     }
                     umma2_commit_mc(bar_tfull + 8 * slot, 3);               // accumulator half complete, both CTAs
-                    if (rec) { long long* d = sch.dbg + 128 + 8 * u; d[0] = a_te; d[1] = a_lr; d[2] = a_fu; d[3] = a_pf; d[4] = a_is; }
                 }
-                if (rec) sch.dbg[63] = clock64();
+                if (rec) dbg_buf[63] = clock64();
             }
         }
     } else if (warp >= 4 && warp < 4 + TC3_EW) {
@@ -559,7 +619,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
             if (ew == 0 && lane == 0) mbar_arrive_cluster(l_lready);
         }
         for (int pt = pt0; pt < n_ptiles; pt += pt_step, ++tcount_e) {
-            const bool rec = sch.dbg && blockIdx.x == 0 && tcount_e == 1 && ew == ((sch.dbg_flags >> 4) & 15) && lane == 0;
+            const bool rec = dbg_buf && blockIdx.x == 0 && tcount_e == 1 && ew == ((dbg_flags >> 4) & 15) && lane == 0;
             const bool has_next = pt + pt_step < n_ptiles;
             float xf_n[BT_MAX_D + 1];
             const int row_n = (pt + pt_step) * P2 + pp;
@@ -579,17 +639,22 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                 const bool release = !(U.flags & TC3_F_HOLD);
                 const uint32_t kabs = (uint32_t)(U.feat0[crank] + lane_r - g0);
                 const float b = gelu_live ? __ldg(sch.bias + kabs) : 0.f;
-                if (is_final) {                                      // features of the next tile, while the last MMAs run
+                const bool pub = (U.flags & TC3_F_PUB) && has_next;
+                if (pub) {                                           // features of the next tile, while this unit's MMAs run
                     tc3_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, row_n < M, xf_n, feat);
                     x0_cur = xf_n[0];
                 }
-                mbar_wait_f(bar_tfull + 8 * slot, par, sch.dbg_flags & 64);
-                mbar_wait_f(bar_tfull + 8 * (slot + 1), par, sch.dbg_flags & 64);
-                if (rec) sch.dbg[64 + 2 * u] = clock64();
-                const bool pub = is_final && has_next;
-                if (pub) { pub_parity = (tcount_e + 1u) & 1u; publish_inputs(); }   // every MMA of this tile has read the buffer
-                if (rec && is_final) sch.dbg[100] = clock64();
+                mbar_wait_f(bar_tfull + 8 * slot, par, dbg_flags & 64);
+                mbar_wait_f(bar_tfull + 8 * (slot + 1), par, dbg_flags & 64);
+                if (rec) dbg_buf[64 + 2 * u] = clock64();
+                if (pub) { pub_parity = (tcount_e + 1u) & 1u; publish_inputs(); }   // every MMA of this tile that reads K-block 0 has completed
                 tc_fence_after();
+                if (gr == 0 && !(is_final && crank == 0) && !pub) {
+                    // this CTA holds no row of the unit: no TMEM reads, no stores, no CTA barrier (its warps may still be
+                    // busy with the previous tile's outputs); one thread hands the accumulator slots back
+                    if (release && ew == 1 && lane == 0) { mbar_arrive_cluster(l_tempty + 8 * slot); mbar_arrive_cluster(l_tempty + 8 * (slot + 1)); }
+                    continue;
+                }
                 // ---- phase 1: accumulators -> registers
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + slot * TC2_BN + (uint32_t)(cq * 32);
                 const int ng = 4 / U.rep, gbeg = ((qd * U.rep) >> 2) * ng;   // replicated units: my groups of 8 columns
@@ -610,7 +675,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                         }
                 } else if (warp_gelu || warp_out) {
                     tmem_ld32(taddr, v);
-                    if (U.two && !(sch.dbg_flags & 2)) {
+                    if (U.two && !(dbg_flags & 2)) {
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             float w[16];
@@ -620,12 +685,11 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                         }
                     }
                 }
-                if (rec && is_final) sch.dbg[101] = clock64();
                 tc_fence_before();
                 // One remote arrival per CTA instead of one per warp: 32 arrivals per barrier per unit (three barriers) serialise
                 // on the leader's mbarriers and made the bare synchronisation skeleton cost ~6 k cycles per unit.
                 asm volatile("bar.sync 2, 512;" ::: "memory");      // all 16 warps have drained this unit's accumulators
-                if (ew == 0 && lane == 0) {
+                if (ew == 1 && lane == 0) {
                     if (release) { mbar_arrive_cluster(l_tempty + 8 * slot); mbar_arrive_cluster(l_tempty + 8 * (slot + 1)); }
                     if (pub) mbar_arrive_cluster(l_lready);          // inputs of the next tile published (fenced before the barrier)
                 }
@@ -634,7 +698,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     const uint32_t kk = kabs % TC_BK, chunk = kk >> 3;
                     const uint32_t dst = act_dst + (kabs / TC_BK) * TC_KB_BYTES + ((kk & 7u) << 1);
                     if (U.rep > 1) {
-                        if (gelu_live && !(sch.dbg_flags & 4)) {
+                        if (gelu_live && !(dbg_flags & 4)) {
 #pragma unroll
                             for (int gg = 0; gg < 2; ++gg)
                                 if (gg < ng) {
@@ -656,7 +720,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                         uint32_t swz[8];
 #pragma unroll
                         for (int r = 0; r < 8; ++r) swz[r] = dst + (uint32_t)(r * 128) + ((chunk ^ (uint32_t)r) << 4);
-                        if (gelu_live && !(sch.dbg_flags & 4)) {
+                        if (gelu_live && !(dbg_flags & 4)) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 float val;
@@ -671,9 +735,8 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                             }
                         }
                     }
-                    if (!(sch.dbg_flags & 1024)) fence_proxy_async();   // CTA-scoped (see mlp_tc2.cuh for why not the cluster form)
+                    if (!(dbg_flags & 1024)) fence_proxy_async();   // CTA-scoped (see mlp_tc2.cuh for why not the cluster form)
                 }
-                if (rec && is_final) sch.dbg[102] = clock64();
                 if (warp_out) {
                     // stage [column][output] fp32 in the last two K-blocks of the activation buffer (every MMA of this tile has
                     // completed; the next tile's last hidden block rewrites them before they are read again), then write the tile's
@@ -685,9 +748,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                         for (int j = 0; j < 32; ++j)                 // row pitch 132 floats: conflict-free
                             asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage_s + (uint32_t)((lane_g * 132 + cq * 32 + j) * 4)), "f"(v[j]) : "memory");
                     }
-                    if (rec) sch.dbg[103] = clock64();
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (rec) sch.dbg[104] = clock64();
                     // thread <-> column of the pair-tile; the n_out values of a column are contiguous in lf / jac
                     const int col = cq * 32 + lane;
                     const int p = col / S, sc = col - p * S, row = pt * P2 + p;
@@ -705,14 +766,13 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                             for (int i = 0; i < 8; ++i) if (f0 + i < no) dst[f0 + i] = o8[i] + add;
                         }
                     }
-                    if (rec) sch.dbg[105] = clock64();
                     // no second barrier: the staging tile is next written a whole tile later
                 }
                 if (U.ready_idx >= 0) {
                     asm volatile("bar.sync 2, 512;" ::: "memory");  // every warp's stores are done and fenced
-                    if (ew == 0 && lane == 0) mbar_arrive_cluster(l_lready + 8 * U.ready_idx);
+                    if (ew == 1 && lane == 0) mbar_arrive_cluster(l_lready + 8 * U.ready_idx);
                 }
-                if (rec) sch.dbg[65 + 2 * u] = clock64();
+                if (rec) dbg_buf[65 + 2 * u] = clock64();
             }
         }
     }
@@ -755,19 +815,27 @@ static inline int tc3_launch(Tc3Net& t, const FmapDev& fm, const NetDev& net, co
     t.sched.dump = dump;
     long long* trace = nullptr;
     int n_chunks = 0;
-    for (int u = 0; u < t.sched.n_units; ++u) n_chunks += (t.sched.U[u].k16_end + 3) / 4 - t.sched.U[u].k16_begin / 4;
+    for (int u = 0; u < t.sched.n_units; ++u) n_chunks += ((t.sched.U[u].k16_end + 3) / 4 - t.sched.U[u].k16_begin / 4 + t.sched.U[u].cw - 1) / t.sched.U[u].cw;
     if (dbg && getenv("BT_TC3_TRACE")) { cudaMalloc(&trace, 768 * sizeof(long long)); cudaMemset(trace, 0, 768 * sizeof(long long)); }
     t.sched.trace = trace;
     t.sched.trace_i0 = n_chunks;
     t.sched.dbg_flags = getenv("BT_TC3_FLAGS") ? atoi(getenv("BT_TC3_FLAGS")) : 0;
     cudaError_t err;
-    if (S == 1) {
-        err = cudaFuncSetAttribute(mlp_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes);
-        if (err == cudaSuccess) mlp_tc3_kernel<1><<<g, TC3_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
-    } else {
-        err = cudaFuncSetAttribute(mlp_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes);
-        if (err == cudaSuccess) mlp_tc3_kernel<4><<<g, TC3_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
-    }
+    const bool use_dbg = dbg || trace || dump || t.sched.dbg_flags;
+#define TC3_LAUNCH(S_, D_)                                                                                                     \
+    do {                                                                                                                       \
+        err = cudaFuncSetAttribute(mlp_tc3_kernel<S_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes);  \
+        if (err == cudaSuccess) mlp_tc3_kernel<S_, D_><<<g, TC3_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac); \
+    } while (0)
+    static const int ko = getenv("BT_TC3_KO") ? atoi(getenv("BT_TC3_KO")) : 0;   // compile-time knock-outs (S = 1 only)
+    if (S == 1 && ko == 4) TC3_LAUNCH(1, 4);
+    else if (S == 1 && ko == 8) TC3_LAUNCH(1, 8);
+    else if (S == 1 && ko == 256) TC3_LAUNCH(1, 256);
+    else if (S == 1 && ko == 268) TC3_LAUNCH(1, 268);
+    else if (S == 1 && ko == 260) TC3_LAUNCH(1, 260);
+    else if (S == 1) { if (use_dbg) TC3_LAUNCH(1, 1); else TC3_LAUNCH(1, 0); }
+    else             { if (use_dbg) TC3_LAUNCH(4, 1); else TC3_LAUNCH(4, 0); }
+#undef TC3_LAUNCH
     if (err != cudaSuccess) return -5;
     if (cudaPeekAtLastError() != cudaSuccess) return -6;
     if (dump) {
@@ -790,24 +858,20 @@ static inline int tc3_launch(Tc3Net& t, const FmapDev& fm, const NetDev& net, co
             cudaMemcpy(tr.data(), trace, 768 * sizeof(long long), cudaMemcpyDeviceToHost);
             cudaFree(trace);
             t.sched.trace = nullptr;
-            fprintf(stderr, "[tc3 chunk trace, cycles since tile start] chunk: issue(own producer) full pfull poll_ok mma_issued retired_seen\n");
+            fprintf(stderr, "[tc3 chunk trace, cycles since tile start] chunk: issue(producer) full mmas_retired(flag 2048) poll_ok mma_issued retired_seen(producer)\n");
             int c = 0;
             for (int u = 0; u < t.sched.n_units; ++u)
-                for (int kb = t.sched.U[u].k16_begin / 4; kb < (t.sched.U[u].k16_end + 3) / 4; ++kb, ++c) {
+                for (int kb = t.sched.U[u].k16_begin / 4; kb < (t.sched.U[u].k16_end + 3) / 4; kb += t.sched.U[u].cw, ++c) {
                     if (c >= 128) break;
                     auto rel = [&](int k) { return tr[k * 128 + c] ? tr[k * 128 + c] - t0 : -1; };
                     fprintf(stderr, "  U%d kb%-2d: %7lld %7lld %7lld %7lld %7lld %7lld\n", u, kb, rel(0), rel(1), rel(2), rel(3), rel(4), rel(5));
                 }
         }
-        fprintf(stderr, "[tc3 issuer0 waits] ");
-        for (int u = 0; u < t.sched.n_units; ++u)
-            fprintf(stderr, "U%d tempty %lld lready %lld full %lld pfull %lld issue %lld | ", u, h[128 + 8 * u], h[129 + 8 * u], h[130 + 8 * u], h[131 + 8 * u], h[132 + 8 * u]);
-        fprintf(stderr, "\n[tc3 timeline S=%d M=%d] MMA thread: ", S, M);
+        fprintf(stderr, "[tc3 timeline S=%d M=%d] MMA thread: ", S, M);
         for (int u = 0; u < t.sched.n_units; ++u) fprintf(stderr, "U%d start %lld ready %lld | ", u, h[1 + 2 * u] - t0, h[2 + 2 * u] ? h[2 + 2 * u] - t0 : -1);
         fprintf(stderr, "end %lld\n[tc3 timeline] epilogue warp4: ", h[63] - t0);
         for (int u = 0; u < t.sched.n_units; ++u) fprintf(stderr, "U%d full %lld done %lld | ", u, h[64 + 2 * u] - t0, h[65 + 2 * u] ? h[65 + 2 * u] - t0 : -1);
-        fprintf(stderr, "\n[tc3 final unit, warp 4] publish %lld tmem %lld release %lld staged %lld barrier %lld stored %lld\n", h[100] - t0, h[101] - t0,
-                h[102] - t0, h[103] - t0, h[104] - t0, h[105] - t0);
+        fprintf(stderr, "\n");
     }
     return 0;
 }

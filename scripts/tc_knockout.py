@@ -18,5 +18,5 @@ for _ in range(3):
     dev.forward_map(theta, compute_derivatives=jac)
 ms, rows, launches = dev.mlp_profile(True, False)
 cols = Mrows * (4 if jac else 1)
-print(f"variant {os.environ.get('BT_TC_VARIANT','1')} flags {os.environ.get('BT_TC3_FLAGS','0')} norep {os.environ.get('BT_TC3_NOREP','-')} nofold {os.environ.get('BT_TC3_NOFOLD','-')}: "
+print(f"variant {os.environ.get('BT_TC_VARIANT','1')} ko {os.environ.get('BT_TC3_KO','0')} flags {os.environ.get('BT_TC3_FLAGS','0')} norep {os.environ.get('BT_TC3_NOREP','-')} nofold {os.environ.get('BT_TC3_NOFOLD','-')}: "
       f"{ms / launches:.3f} ms per launch, {cols / (ms / launches) / 1e3:.1f} M columns/s, cycles per 128 columns per SM pair @1.9GHz: {ms / launches * 1e-3 * 1.9e9 / (cols / 128 / 74):.0f}")
