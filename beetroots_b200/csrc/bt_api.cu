@@ -161,6 +161,15 @@ extern "C" int bt_set_mlp_mode(bt_ctx* c, int mode) {
 }
 extern "C" int bt_synchronize(bt_ctx* c) { REQUIRE(c, "null ctx"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return 0; }
 extern "C" int64_t bt_kernel_launches(bt_ctx* c) { return c ? c->launches : -1; }
+// which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 3 = pair kernel (mlp_tc3.cuh, default),
+// 1 = single-CTA kernel (mlp_tc.cuh; also the fallback for shapes the pair kernel does not take), 2 = first cta_group::2 kernel
+static int tc_variant(const bt_ctx* c) {
+    static const int want = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 3;
+    if (want == 3 && c->tc3.ready) return 3;
+    if (want == 2 && c->tc2.ready) return 2;
+    return c->tc.ready ? 1 : 0;
+}
+extern "C" int bt_mlp_kernel_variant(bt_ctx* c) { return c ? tc_variant(c) : -1; }
 
 template <typename T>
 static int upload(T** dst, const std::vector<T>& h, std::vector<void*>* track) {
@@ -392,10 +401,10 @@ static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
         CK(cudaEventRecord(e0, c->stream));
     }
     if (c->mlp_mode == BT_MLP_BF16_TC) {
-        static const int variant = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 3;   // 3 = pair kernel (mlp_tc3.cuh, default), 1 = single-CTA kernel, 2 = first cta_group::2 kernel
-        int rc = (variant == 3 && c->tc3.ready) ? tc3_launch(c->tc3, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
-               : (variant == 2 && c->tc2.ready) ? tc2_launch(c->tc2, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
-                                                : tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);
+        const int variant = tc_variant(c);
+        int rc = variant == 3 ? tc3_launch(c->tc3, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
+               : variant == 2 ? tc2_launch(c->tc2, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
+                              : tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);
         if (rc) return fail("tensor-core MLP launch failed", __FILE__, __LINE__);
         KLAUNCH(c);
     } else {

@@ -435,12 +435,14 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     const uint32_t bytes_kb = (uint32_t)U.groups[crank] * 1024u;
                     const uint8_t* src = sch.wstream[crank] + (size_t)U.w_off[crank] * 1024;
                     const int kb1 = (U.k16_end + 3) >> 2;
-                    const uint32_t win = (uint32_t)U.cw * 16384u;
+                    // operand windows: K-block q of a chunk is read as 128 rows (16 KB) from pos + q * adv_kb; the last one may run
+                    // up to TC3_MISC_BYTES past the ring (into misc: garbage rows feed accumulator lanes nobody reads)
+                    const uint32_t win = (uint32_t)(U.cw - 1) * adv_kb + 16384u - TC3_MISC_BYTES;
                     for (int kb = U.k16_begin >> 2; kb < kb1; kb += U.cw, ++i) {
                         const uint32_t nk = (uint32_t)(kb1 - kb < U.cw ? kb1 - kb : U.cw);
                         const uint32_t adv = adv_kb * nk, bytes = bytes_kb * nk;
                         // the 128-row operand windows (16 KB per K-block) must end inside the ring; chunks of this unit start at >= ring_lo
-                        if (pos + win > ring_bytes) { vpos += ring_bytes - pos; pos = 0; }
+                        if (pos + win > ring_bytes || pos + adv > ring_bytes) { vpos += ring_bytes - pos; pos = 0; }   // data and operand windows fit
                         if (pos < (uint32_t)U.ring_lo) { vpos += (uint32_t)U.ring_lo - pos; pos = (uint32_t)U.ring_lo; }
                         const uint32_t t = i % TC3_NT;
                         if (i % TC3_NPROD != pid) {                          // somebody else's chunk: just remember where it lives
@@ -529,12 +531,12 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     const uint32_t d_tmem = tmem_base + slot * TC2_BN;
                     bool waited = false;
                     const int kb0 = U.k16_begin >> 2, kb1 = (U.k16_end + 3) >> 2, cw = U.cw;
-                    const uint32_t ring_lo = (uint32_t)U.ring_lo, win = (uint32_t)cw * 16384u;
+                    const uint32_t ring_lo = (uint32_t)U.ring_lo, win = (uint32_t)(cw - 1) * adv + 16384u - TC3_MISC_BYTES;
                     const int k16b = U.k16_begin, k16e = U.k16_end, new_k16 = U.new_k16;
                     int ci = 0;
                     for (int kbc = kb0; kbc < kb1; kbc += cw, ++i, ++ci) {
                         const int nk = kb1 - kbc < cw ? kb1 - kbc : cw;
-                        if (pos + win > ring_bytes) pos = 0;
+                        if (pos + win > ring_bytes || pos + adv * (uint32_t)nk > ring_bytes) pos = 0;
                         if (pos < ring_lo) pos = ring_lo;
                         const uint32_t cur = pos;
                         pos += adv * (uint32_t)nk;
@@ -688,10 +690,15 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                 tc_fence_before();
                 // One remote arrival per CTA instead of one per warp: 32 arrivals per barrier per unit (three barriers) serialise
                 // on the leader's mbarriers and made the bare synchronisation skeleton cost ~6 k cycles per unit.
-                asm volatile("bar.sync 2, 512;" ::: "memory");      // all 16 warps have drained this unit's accumulators
-                if (ew == 1 && lane == 0) {
-                    if (release) { mbar_arrive_cluster(l_tempty + 8 * slot); mbar_arrive_cluster(l_tempty + 8 * (slot + 1)); }
-                    if (pub) mbar_arrive_cluster(l_lready);          // inputs of the next tile published (fenced before the barrier)
+                // ONE CTA barrier per unit (after the stores): accumulator slots, next-tile inputs and this unit's features are
+                // all handed over together by one thread.  The slots of unit u are next needed by unit u + 2, long after.
+                if (is_final && pub) {                               // (only when the output layer is not folded)
+                    asm volatile("bar.sync 2, 512;" ::: "memory");
+                    if (ew == 1 && lane == 0) mbar_arrive_cluster(l_lready);
+                }
+                if (is_final && crank != 0 && ew == 1 && lane == 0) {   // the peer reads nothing of the final accumulators
+                    mbar_arrive_cluster(l_tempty + 8 * slot);
+                    mbar_arrive_cluster(l_tempty + 8 * (slot + 1));
                 }
                 // ---- phase 2: activation, stores
                 if (warp_gelu) {
@@ -749,6 +756,8 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                             asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage_s + (uint32_t)((lane_g * 132 + cq * 32 + j) * 4)), "f"(v[j]) : "memory");
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // the four output warps are the only readers of the final accumulators in this CTA: slots free again
+                    if (cq == 0 && lane == 0) { mbar_arrive_cluster(l_tempty + 8 * slot); mbar_arrive_cluster(l_tempty + 8 * (slot + 1)); }
                     // thread <-> column of the pair-tile; the n_out values of a column are contiguous in lf / jac
                     const int col = cq * 32 + lane;
                     const int p = col / S, sc = col - p * S, row = pt * P2 + p;
@@ -768,9 +777,13 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     }
                     // no second barrier: the staging tile is next written a whole tile later
                 }
-                if (U.ready_idx >= 0) {
-                    asm volatile("bar.sync 2, 512;" ::: "memory");  // every warp's stores are done and fenced
-                    if (ew == 1 && lane == 0) mbar_arrive_cluster(l_lready + 8 * U.ready_idx);
+                if (!is_final) {
+                    asm volatile("bar.sync 2, 512;" ::: "memory");  // every warp has drained the accumulators; its stores are done and fenced
+                    if (ew == 1 && lane == 0) {
+                        if (release) { mbar_arrive_cluster(l_tempty + 8 * slot); mbar_arrive_cluster(l_tempty + 8 * (slot + 1)); }
+                        if (pub) mbar_arrive_cluster(l_lready);      // inputs of the next tile
+                        if (U.ready_idx >= 0) mbar_arrive_cluster(l_lready + 8 * U.ready_idx);
+                    }
                 }
                 if (rec) dbg_buf[65 + 2 * u] = clock64();
             }

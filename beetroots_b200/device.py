@@ -309,6 +309,10 @@ class DevicePosterior:
     def kernel_launches(self) -> int:
         return int(self._lib.bt_kernel_launches(self._ctx))
 
+    def mlp_kernel_variant(self) -> int:
+        """Tensor-core forward-map kernel in use for this network (3 = pair kernel, 1 = single-CTA kernel, 0 = none)."""
+        return int(self._lib.bt_mlp_kernel_variant(self._ctx))
+
     def mlp_profile(self, enable=True, reset=False):
         ms, rows, launches = C.c_double(), C.c_int64(), C.c_int64()
         L.check(self._lib.bt_mlp_profile(self._ctx, int(enable), int(reset), C.byref(ms), C.byref(rows),

@@ -155,6 +155,9 @@ int bt_model_check_reset(bt_ctx* ctx);
 int bt_model_check_update(bt_ctx* ctx, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject);
 int bt_model_check_get(bt_ctx* ctx, double* clppd, double* pval_y, double* pval_llh, int finalize);
 
+/* which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 3 = pair kernel (default),
+ * 1 = single-CTA kernel (fallback for shapes the pair kernel does not take), 2 = first cta_group::2 kernel, 0 = none. */
+int bt_mlp_kernel_variant(bt_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t bt_kernel_launches(bt_ctx* ctx);
 /* device time (ms) spent in the forward-map kernel since the last call with reset != 0 and the

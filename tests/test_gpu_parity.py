@@ -432,6 +432,53 @@ def test_tensor_core_variants_agree(lib):
     assert np.abs(outs[2]["jac"] - outs[0]["jac"]).max() < 5e-3 * max(1.0, np.abs(outs[0]["jac"]).max())
 
 
+@pytest.mark.parametrize("arch,env", [
+    ((10, 0.5, 10), {}),                                  # the reference architecture, default schedule
+    ((10, 0.5, 10), {"BT_TC3_NOFOLD": "1"}),              # output layer as a unit of its own
+    ((10, 0.5, 10), {"BT_TC3_NOREP": "1"}),               # no row replication in the small units
+    ((10, 0.5, 10), {"BT_TC3_NOEXT": "1"}),               # weight ring confined to its own shared memory
+    ((10, 0.5, 10), {"BT_TC3_CW": "1"}),                  # one K-block per weight chunk
+    ((10, 0.5, 32), {}),                                  # maximum number of lines
+    ((7, 0.5, 5), {}),                                    # shallow network: every block is a "small" unit
+    ((6, 1.0, 7), {}),                                    # legacy dense architecture: widths double, last block = 3 units
+    ((9, 0.5, 3), {}),
+])
+def test_pair_kernel_schedules_and_architectures(lib, arch, env):
+    """The unit schedule of the default tensor-core kernel (mlp_tc3.cuh: folding, replication, chunk width, ring
+    extension) is built from the network shape; every variant of it must reproduce the fp32 CUDA-core kernel to the
+    bf16 bound, with and without the Jacobian, on ragged row counts."""
+    import subprocess
+    import sys
+    import os
+    n_layers, growing, n_out = arch
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from beetroots_b200 import modelling as M, DevicePosterior, MLP_BF16_TC, MLP_FP32\n"
+        "from beetroots_b200.network import synthetic_weights\n"
+        "L = %d\n"
+        "net = synthetic_weights(3, L, n_layers=%d, growing_factor=%r)\n"
+        "fm = M.NeuralNetworkApprox(net, {'kappa': None, 'P': None, 'radm': None, 'Avmax': None, 'angle': -1.5})\n"
+        "lik = M.MixingModelsLikelihood(fm, 4, L, 8, np.ones((8, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)), a1=np.ones((1, L)))\n"
+        "dev = DevicePosterior.from_posterior(M.Posterior(4, L, 8, lik, None, None))\n"
+        "assert dev.mlp_kernel_variant() == 3, dev.mlp_kernel_variant()\n"
+        "worst = 0.0\n"
+        "for Mr, jac in ((1, False), (257, True), (20011, False), (5003, True)):\n"
+        "    th = np.random.default_rng(Mr).uniform(-1.5, 1.5, size=(Mr, 4))\n"
+        "    dev.set_mlp_mode(MLP_FP32); ref = dev.forward_map(th, compute_derivatives=jac)\n"
+        "    dev.set_mlp_mode(MLP_BF16_TC); out = dev.forward_map(th, compute_derivatives=jac)\n"
+        "    e = np.abs(out['log_f_Theta'] - ref['log_f_Theta']).max()\n"
+        "    if jac: e = max(e, np.abs(out['grad_log_f_Theta'] - ref['grad_log_f_Theta']).max() / max(1.0, np.abs(ref['grad_log_f_Theta']).max()))\n"
+        "    worst = max(worst, float(e))\n"
+        "print('WORST', worst)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n_out, n_layers, growing)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BT_TC_VARIANT="3", **env), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst < 4e-2, worst            # bf16 operands, fp32 accumulation: ~1e-2 in ln f on the reference architecture
+
+
 def test_model_check_vs_oracle(lib):
     """Online model checking (clppd, Bayesian p-values; my_sampler.py:158-267) with injected replication noise."""
     from beetroots_b200 import DevicePosterior
