@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbeetroots_b200.so")
+LIB_PATH = os.environ.get("BT_LIB_PATH", os.path.join(_HERE, "libbeetroots_b200.so"))   # override: A/B runs of two builds
 
 _lib = None
 

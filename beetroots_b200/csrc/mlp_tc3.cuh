@@ -27,13 +27,19 @@
 #define TC3_F_PUB 8                // after this unit's accumulators complete nothing of this tile reads K-block 0 any more: publish the next tile's inputs
 #define TC3_F_FINAL 4              // lanes [0, n_out) of CTA 0 hold the finished output layer
 #define TC3_MISC_BYTES 4096
+#ifndef TC3_UNIFORM_ISSUER
+#define TC3_UNIFORM_ISSUER 1
+#endif
+#ifndef TC3_ISSUER_SPIN
+#define TC3_ISSUER_SPIN 0         // MMA issuers busy-poll their barriers (test_wait): try_wait parks the thread and was seen to wake late
+#endif
 
 struct Tc3Unit {
     short k16_begin, k16_end;      // K range of this unit's MMAs, in steps of 16 features
     short new_k16;                 // first step holding features guarded by ready barrier `dep`
     short dep, sp, flags, ready_idx, two;
     int ring_lo;                   // chunks of this unit may live in [ring_lo, ring_bytes) of the extended ring
-    short cw;                      // K-blocks per weight chunk (handshake granularity): 1 or 2
+    short cw;                      // K-blocks per weight chunk (handshake granularity): 1, 2 or 4
     short rep;                     // small units: the rows are replicated in rep lane groups, each handles 32/rep of a warp's columns
     short groups[2];               // 8-row groups of weights streamed per K-block, per CTA
     short gelu_lane0[2], gelu_rows[2];
@@ -140,9 +146,7 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
         w += nnew;
     }
     const int prev_in_saved = prev_in;
-    // the extension is used by the units with big chunks only (from the first unit with >= 8 KB chunks on)
-    int first_ext_unit = nu;
-    for (int u = 0; u < nu; ++u) if (std::max<int>(s.U[u].groups[0], s.U[u].groups[1]) >= 12 && s.U[u].rep == 1) { first_ext_unit = u; break; }
+    int first_ext_unit = nu;   // set below: first unit issued at least one ring of chunk bytes after the tile's first chunk
     {   // output layer: continuation of the folded unit, or a unit of its own
         const int in_last = prev_in;                 // features available before the last hidden block's outputs
         Tc3Unit& U = s.U[nu];
@@ -175,13 +179,15 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
     // K-blocks stream two K-blocks per chunk.  Both CTAs then stream the same number of 8-row groups (zero rows pad the
     // smaller half) so that the second K-block sits at the same offset in both.
     {
-        static const int cw_env = getenv("BT_TC3_CW") ? atoi(getenv("BT_TC3_CW")) : 2;
+        static const int cw_env = getenv("BT_TC3_CW") ? atoi(getenv("BT_TC3_CW")) : 4;
         for (int u = 0; u < nu; ++u) {
             Tc3Unit& U = s.U[u];
             const int nkb = (U.k16_end + 3) / 4 - U.k16_begin / 4;
+            const int gmax = std::max<int>(U.groups[0], U.groups[1]);
             U.cw = (short)((cw_env >= 2 && nkb >= 4) ? 2 : 1);
+            if (cw_env >= 4 && nkb >= 8 && gmax * 4 <= 32) U.cw = 4;       // <= 32 KB per chunk, still >= 2 chunks (both issuers)
             if (!(U.flags & TC3_F_CONT) && !(U.flags & TC3_F_FINAL)) U.two = (short)((nkb + U.cw - 1) / U.cw >= 2);
-            if (U.cw == 2) {
+            if (U.cw >= 2) {
                 const short g = std::max(U.groups[0], U.groups[1]);
                 for (int c = 0; c < 2; ++c) {
                     U.groups[c] = g;
@@ -215,6 +221,13 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
         s.ring_bytes = ring_own + ext;
         long bytes_before = 0;
         bool ok = true;
+        {
+            long acc_b = 0;
+            for (int u = 0; u < nu; ++u) {
+                if (acc_b >= ring_own + ext) { first_ext_unit = u; break; }
+                acc_b += 1024L * std::max<int>(s.U[u].groups[0], s.U[u].groups[1]) * ((s.U[u].k16_end + 3) / 4 - s.U[u].k16_begin / 4);
+            }
+        }
         for (int u = 0; u < nu; ++u) {
             Tc3Unit& U = s.U[u];
             const int nkb = (U.k16_end + 3) / 4 - U.k16_begin / 4;
@@ -350,6 +363,11 @@ __device__ __forceinline__ void umma2_f16_lo(uint32_t d_tmem, uint32_t a_lo, uin
         "mov.b64 db, {%2, %3};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mbar_wait_f(uint32_t bar, uint32_t parity, bool spin) {
     if (spin) mbar_spin(bar, parity); else mbar_wait(bar, parity);
@@ -508,13 +526,16 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
     } else if (warp == 1 || warp == 2) {
         // ===================== MMA issuers (leader CTA only), K-blocks split by parity over two threads =====================
         const int par = warp - 1;
-        if (lane == 0 && crank == 0) {
+        // The whole warp runs the (warp-uniform) issue loop and ONE elected lane executes the tcgen05 instructions: with a
+        // single active lane the compiler cannot prove uniformity and wraps every MMA in vector->uniform register moves.
+        if ((TC3_UNIFORM_ISSUER || lane == 0) && crank == 0) {
+            const bool leader_lane = TC3_UNIFORM_ISSUER ? elect_one() : true;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(TC2_BM >> 4) << 24);
             const uint32_t act_addr = smem_u32(act), ring_addr = smem_u32(ring);
             const uint32_t desc_lo0 = 1u << 16, desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // umma_desc_sw128(0), split in words
             uint32_t i = 0, pos = 0, nacq0 = 0, nacq1 = 0, tcount = 0, ready_seen = 0;
             for (int pt = pt0; pt < n_ptiles; pt += pt_step, ++tcount) {
-                const bool rec = dbg_buf && blockIdx.x == 0 && tcount == 1 && par == 0;
+                const bool rec = dbg_buf && blockIdx.x == 0 && tcount == 1 && par == ((dbg_flags >> 12) & 1) && lane == 0;   // flag 4096: trace the second issuer
                 if (rec) dbg_buf[0] = clock64();
                 for (int u = 0; u < sch.n_units; ++u) {
                     const Tc3Unit U = sch.U[u];
@@ -524,7 +545,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     uint32_t acc = 1u;
                     if (!(U.flags & TC3_F_CONT)) {
                         const uint32_t k = U.sp ? nacq1++ : nacq0++;
-                        mbar_wait_f(bar_tempty + 8 * slot, (k & 1u) ^ 1u, dbg_flags & 32);
+                        mbar_wait_f(bar_tempty + 8 * slot, (k & 1u) ^ 1u, TC3_ISSUER_SPIN || (dbg_flags & 32));
                         tc_fence_after();
                         acc = 0u;
                     }
@@ -548,7 +569,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                             const int ks_lo = kb == kb0 ? (k16b & 3) : 0;
                             const int ks_hi = kb == kb1 - 1 ? k16e - 4 * kb : 4;
                             if (!waited && 4 * kb + ks_hi > new_k16) {
-                                mbar_wait_f(bar_lready + 8 * U.dep, tcount & 1u, dbg_flags & 32);
+                                mbar_wait_f(bar_lready + 8 * U.dep, tcount & 1u, TC3_ISSUER_SPIN || (dbg_flags & 32));
                                 if (rec) dbg_buf[2 + 2 * u] = clock64();
                                 waited = true;
                             }
@@ -556,13 +577,13 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                                 while ((int32_t)(ready_seen - (i + 1u)) < 0)     // weights of chunk i landed in both CTAs?
                                     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ready_seen) : "r"(ready_cnt) : "memory");
                                 polled = true;
-                                const bool tr = trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
+                                const bool tr = trace_buf && lane == 0 && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
                                 if (tr) trace_buf[384 + i - sch.trace_i0] = clock64();
                             }
                             // descriptors differ only in the 14-bit start-address field of the low word
                             const uint32_t a_lo = desc_lo0 + ((ring_addr + cur + (uint32_t)q * adv) >> 4);
                             const uint32_t b_lo = desc_lo0 + ((act_addr + kb * TC_KB_BYTES) >> 4);
-                            if (!(dbg_flags & 8)) {
+                            if (!(dbg_flags & 8) && leader_lane) {
                                 if (ks_lo == 0 && ks_hi == 4) {
                                     umma2_f16_lo(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
                                     umma2_f16_lo(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
@@ -576,10 +597,12 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                                 }
                             }
                         }
-                        umma2_commit_mc(bar_empty + 8 * t, 3);              // frees the chunk in both CTAs
-                        if (trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u) trace_buf[512 + i - sch.trace_i0] = clock64();
+                        if (leader_lane) umma2_commit_mc(bar_empty + 8 * t, 3);   // frees the chunk in both CTAs
+                        if (TC3_UNIFORM_ISSUER) __syncwarp();
+                        if (trace_buf && lane == 0 && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u) trace_buf[512 + i - sch.trace_i0] = clock64();
                     }
-                    umma2_commit_mc(bar_tfull + 8 * slot, 3);               // accumulator half complete, both CTAs
+                    if (leader_lane) umma2_commit_mc(bar_tfull + 8 * slot, 3);   // accumulator half complete, both CTAs
+                    if (TC3_UNIFORM_ISSUER) __syncwarp();
                 }
                 if (rec) dbg_buf[63] = clock64();
             }
