@@ -869,6 +869,7 @@ static inline int tc3_launch(Tc3Net& t, const FmapDev& fm, const NetDev& net, co
     else if (S == 1 && ko == 256) TC3_LAUNCH(1, 256);
     else if (S == 1 && ko == 268) TC3_LAUNCH(1, 268);
     else if (S == 1 && ko == 260) TC3_LAUNCH(1, 260);
+    else if (S == 1 && ko == 1024) TC3_LAUNCH(1, 1024);   // no generic->async proxy fence after the activation stores (results invalid)
     else if (S == 1) { if (use_dbg) TC3_LAUNCH(1, 1); else TC3_LAUNCH(1, 0); }
     else             { if (use_dbg) TC3_LAUNCH(4, 1); else TC3_LAUNCH(4, 0); }
 #undef TC3_LAUNCH
