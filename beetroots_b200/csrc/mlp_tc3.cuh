@@ -27,6 +27,9 @@
 #define TC3_F_PUB 8                // after this unit's accumulators complete nothing of this tile reads K-block 0 any more: publish the next tile's inputs
 #define TC3_F_FINAL 4              // lanes [0, n_out) of CTA 0 hold the finished output layer
 #define TC3_MISC_BYTES 4096
+#ifndef TC3_GATE
+#define TC3_GATE 0                 // 1: one polling warp + bar.sync gate for the accumulator barriers -- measured 4 % slower than 16 try_waits
+#endif
 #ifndef TC3_UNIFORM_ISSUER
 #define TC3_UNIFORM_ISSUER 1
 #endif
@@ -123,7 +126,10 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
             // (identical MMA cost, M is 256 anyway) and let every group convert a share of the columns.
             static const bool norep = getenv("BT_TC3_NOREP") != nullptr;
             const int rmax = std::max<int>(U.gelu_rows[0], U.gelu_rows[1]);
-            U.rep = (short)((fold || norep) ? 1 : (rmax <= 32 ? 4 : (rmax <= 64 ? 2 : 1)));
+            // (only for units with a short K loop: replication multiplies the weight bytes, and a unit with many K-blocks is
+            // paced by its weight stream, not by its epilogue)
+            const int nkb_u = (U.k16_end + 3) / 4;
+            U.rep = (short)((fold || norep || nkb_u > 4) ? 1 : (rmax <= 32 ? 4 : (rmax <= 64 ? 2 : 1)));
             const int span = 128 / U.rep;
             U.groups[0] = (short)(U.rep == 1 ? t0 : (U.gelu_rows[0] ? (span * (U.rep - 1) + U.gelu_rows[0] + 7) / 8 : 0));
             U.groups[1] = (short)(U.rep == 1 ? (U.gelu_rows[1] + 7) / 8 : (U.gelu_rows[1] ? (span * (U.rep - 1) + U.gelu_rows[1] + 7) / 8 : 0));
@@ -669,8 +675,15 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     tc3_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, row_n < M, xf_n, feat);
                     x0_cur = xf_n[0];
                 }
+#if TC3_GATE
+                // ONE warp busy-polls the accumulator barriers and releases the other 15 through a hardware barrier: a warp parked
+                // in mbarrier.try_wait was measured to resume ~550 cycles after the phase completes, once per unit on the critical path
+                if (ew == 1) { mbar_spin(bar_tfull + 8 * slot, par); mbar_spin(bar_tfull + 8 * (slot + 1), par); }
+                asm volatile("bar.sync 3, 512;" ::: "memory");
+#else
                 mbar_wait_f(bar_tfull + 8 * slot, par, dbg_flags & 64);
                 mbar_wait_f(bar_tfull + 8 * (slot + 1), par, dbg_flags & 64);
+#endif
                 if (rec) dbg_buf[64 + 2 * u] = clock64();
                 if (pub) { pub_parity = (tcount_e + 1u) & 1u; publish_inputs(); }   // every MMA of this tile that reads K-block 0 has completed
                 tc_fence_after();
