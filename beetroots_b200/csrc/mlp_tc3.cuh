@@ -50,6 +50,7 @@ struct Tc3Unit {
     int w_off[2];                  // 1 KB units into CTA c's weight stream
 };
 struct Tc3Sched {
+    int stage_kb;                  // first of the 3 K-blocks used as output staging tile by the final epilogue
     int n_units, n_ready, act_kb, n_out, ring_bytes, ring_ext;   // ring_bytes includes ring_ext bytes borrowed from the tail of act
     int ready_count[TC_MAX_LAYERS + 1];
     Tc3Unit U[TC3_MAX_UNITS];
@@ -90,10 +91,12 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
     int w = n_feat0, prev_in = 0, nu = 0, n_feat = n_feat0;
     for (int l = 0; l < n_blocks; ++l) n_feat += block_new[l];
     bool folded = false;
+    int layer_in_of_last_minus_1 = n_feat0;
     int unit_layer[TC3_MAX_UNITS], unit_mt[TC3_MAX_UNITS];
     for (int u = 0; u < TC3_MAX_UNITS; ++u) { unit_layer[u] = -1; unit_mt[u] = 0; }
     for (int l = 0; l < n_blocks; ++l) {
         const int in = w, nnew = block_new[l];
+        if (l == n_blocks - 2) layer_in_of_last_minus_1 = in;
         const int n_mt = (nnew + 255) / 256;
         for (int mt = 0; mt < n_mt; ++mt) {
             if (nu >= TC3_MAX_UNITS - 1) return 0;
@@ -223,6 +226,17 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
         const int in_last = prev_in_saved;
         const int kb_first = (in_last + TC_BK - 1) / TC_BK;          // K-blocks [kb_first, act_kb) hold only last-block outputs
         int ext = noext ? 0 : (s.act_kb - kb_first) * TC_KB_BYTES;
+        // Output staging tile of the final epilogue (<= 17 KB = 3 K-blocks): it must not be ring space (the producer may
+        // already stream next-tile chunks into the extension), and nothing may read it before it is rewritten in the next
+        // tile.  K-blocks that hold only outputs of the last two hidden blocks qualify: they are rewritten by those blocks'
+        // epilogues before any unit reads them again.  Otherwise: staging in the tail of act and no ring extension.
+        {
+            const int in_prev = n_blocks >= 2 ? layer_in_of_last_minus_1 : n_feat0;
+            const int kb_lo = (in_prev + TC_BK - 1) / TC_BK;
+            if (kb_first - 3 >= kb_lo && kb_first - 3 >= 1) s.stage_kb = kb_first - 3;
+            else { s.stage_kb = s.act_kb - 3; ext = 0; }
+            if (s.stage_kb < 1) return 0;
+        }
         s.ring_ext = ext;
         s.ring_bytes = ring_own + ext;
         long bytes_before = 0;
@@ -784,7 +798,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     // stage [column][output] fp32 in the last two K-blocks of the activation buffer (every MMA of this tile has
                     // completed; the next tile's last hidden block rewrites them before they are read again), then write the tile's
                     // outputs with coalesced stores: lf rows and jac rows of a tile are contiguous in global memory
-                    const uint32_t stage_s = act_s + (uint32_t)(sch.act_kb - 3) * TC_KB_BYTES;   // [n_out][132] floats <= 17 KB
+                    const uint32_t stage_s = act_s + (uint32_t)sch.stage_kb * TC_KB_BYTES;   // [n_out][132] floats <= 17 KB, see tc3_build
                     const int no = sch.n_out;
                     if (lane_g < no) {
 #pragma unroll
