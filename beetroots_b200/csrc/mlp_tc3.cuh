@@ -17,8 +17,8 @@
 #pragma once
 #include "mlp_tc2.cuh"
 
-#define TC3_NPROD 1                 // weight-producer threads (warp 0 and the two warps after the epilogue warps)
-#define TC3_THREADS (128 + 32 * TC3_EW + 32 * (TC3_NPROD - 1))
+#define TC3_NPROD 2                 // weight-producer threads (warp 0 and the two warps after the epilogue warps)
+#define TC3_THREADS (128 + 32 * TC3_EW)
 #define TC3_EW 16                  // epilogue warps per CTA
 #define TC3_NT 16                  // weight chunks in flight (tickets)
 #define TC3_MAX_UNITS 24
@@ -415,7 +415,6 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC3_NT), bar_pfull = smem_u32(bars + 2 * TC3_NT);
     const uint32_t bar_tfull = smem_u32(bars + 3 * TC3_NT), bar_tempty = smem_u32(bars + 3 * TC3_NT + 4);
     const uint32_t bar_lready = smem_u32(bars + 3 * TC3_NT + 8);
-    const uint32_t ready_cnt = smem_u32(misc + 1004);              // chunks landed in both CTAs (leader)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -429,7 +428,6 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
         for (int i = 0; i < 3 * TC3_NT; ++i) mbar_init(bar_full + 8 * i, (i < TC3_NT && crank == 0) ? 2 : 1);
         for (int i = 0; i < 4; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 2); }
         for (int l = 0; l < sch.n_ready; ++l) mbar_init(bar_lready + 8 * l, sch.ready_count[l]);
-        *reinterpret_cast<volatile uint32_t*>(misc + 1004) = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -453,12 +451,15 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    if (warp == 0 || warp >= 4 + TC3_EW) {
+    const bool second_producer = TC3_NPROD == 2 && ((crank == 0 && warp == 3) || (crank == 1 && warp == 1));
+    if (warp == 0 || second_producer) {
         // ===================== weight producers (both CTAs, own rows of every unit) =====================
-        // One cp.async.bulk occupies the issuing thread for ~450 cycles whatever its size (scripts/bulk_bench.cu: one
-        // thread sustains 37 B/clk with 16 KB copies, four warps 119 B/clk), so TC3_NPROD threads take the chunks round robin.
+        // Issuing a bulk copy costs the thread ~80 cycles, but the copies of ONE warp complete one after the other (~450
+        // cycles each whatever their size, scripts/tma_bench.cu) while copies of different warps overlap: two producer
+        // warps take the chunks alternately.  The second one is a warp that has nothing else to do: warp 3 in the leader
+        // (the MMA issuers poll the "full" barriers themselves), warp 1 in the peer (MMAs are issued by the leader only).
         // Every producer walks the whole schedule (positions are deterministic) and retires chunks on its own.
-        const uint32_t pid = warp == 0 ? 0u : (uint32_t)(warp - (4 + TC3_EW) + 1);
+        const uint32_t pid = warp == 0 ? 0u : 1u;
         uint32_t* cst = cst_all + pid * TC3_NT;
         if (lane == 0) {
             const uint32_t ring_addr = smem_u32(ring);
@@ -511,23 +512,6 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                     }
                 }
         }
-    } else if (warp == 3 && crank == 0) {
-        // ===================== leader: "chunk i has landed in both CTAs" -> one counter the MMA issuers poll =====================
-        // (an mbarrier wait on the issuing thread costs ~200 cycles per chunk even when the phase is already complete)
-        if (lane == 0) {
-            uint32_t i = 0;
-            for (int pt = pt0; pt < n_ptiles; pt += pt_step)
-                for (int u = 0; u < sch.n_units; ++u) {
-                    const int n = (((sch.U[u].k16_end + 3) >> 2) - (sch.U[u].k16_begin >> 2) + sch.U[u].cw - 1) / sch.U[u].cw;
-                    for (int k = 0; k < n; ++k, ++i) {
-                        const uint32_t t = i % TC3_NT, ph = (i / TC3_NT) & 1u;
-                        const bool tr = trace_buf && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
-                        mbar_spin(bar_full + 8 * t, ph);
-                        if (tr) trace_buf[128 + i - sch.trace_i0] = clock64();
-                        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ready_cnt), "r"(i + 1u) : "memory");
-                    }
-                }
-        }
     } else if (warp == 3) {
         // ===================== relay (peer CTA): "my chunk has landed" -> leader =====================
         if (lane == 0 && crank == 1) {
@@ -553,7 +537,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(TC2_BM >> 4) << 24);
             const uint32_t act_addr = smem_u32(act), ring_addr = smem_u32(ring);
             const uint32_t desc_lo0 = 1u << 16, desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // umma_desc_sw128(0), split in words
-            uint32_t i = 0, pos = 0, nacq0 = 0, nacq1 = 0, tcount = 0, ready_seen = 0;
+            uint32_t i = 0, pos = 0, nacq0 = 0, nacq1 = 0, tcount = 0;
             for (int pt = pt0; pt < n_ptiles; pt += pt_step, ++tcount) {
                 const bool rec = dbg_buf && blockIdx.x == 0 && tcount == 1 && par == ((dbg_flags >> 12) & 1) && lane == 0;   // flag 4096: trace the second issuer
                 if (rec) dbg_buf[0] = clock64();
@@ -594,8 +578,7 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                                 waited = true;
                             }
                             if (!polled) {
-                                while ((int32_t)(ready_seen - (i + 1u)) < 0)     // weights of chunk i landed in both CTAs?
-                                    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ready_seen) : "r"(ready_cnt) : "memory");
+                                mbar_spin(bar_full + 8 * t, (i / TC3_NT) & 1u);     // weights of chunk i landed in both CTAs (2 arrivals)
                                 polled = true;
                                 const bool tr = trace_buf && lane == 0 && blockIdx.x == 0 && i - (uint32_t)sch.trace_i0 < 128u;
                                 if (tr) trace_buf[384 + i - sch.trace_i0] = clock64();
