@@ -177,33 +177,44 @@ __device__ __forceinline__ void mixing_line(float lf, const ObsConst& o, float& 
     }
     const float da = o.yr - r;                    // (y - f - m_a) / sigma_a, m_a = 0  :1055
     const float za = da / sar;
-    const float ln_sa = o.lsa0 + 0.5f * logf(sar2);    // ln s_a (true scale)
-    const float nll_au = 0.5f * za * za + ln_sa;                    // :14-19
-    const float nll_ac = nan_to_num(-log_ndtr_f(za));               // :574-585 with y in the omega slot (:1212)
-    const float dm = o.ly - lf - m_m;
-    const float nll_mu = 0.5f * dm * dm / sm2_ + 0.5f * logf(sm2_);   // :22-33
-    const float zmc = (o.lw - lf - m_m) / s_m;
-    const float nll_mc = nan_to_num(-log_ndtr_f(zmc));              // :604-616
-    const bool cens = o.flags & 1u;
+    // The reference evaluates the four negative log-densities (additive / multiplicative x uncensored / censored) and
+    // SELECTS two of them by y <= omega (value) and two by y == omega (gradient, :655).  The flags are constants of the
+    // (pixel, line), i.e. uniform over the warp's candidates: the pair that is not selected is never computed (exactly the
+    // same result; the censored pair costs two log_ndtr evaluations).
+    const bool cens = o.flags & 1u, eq = o.flags & 2u;
+    const bool need_c = cens || (WITH_GRAD && eq), need_u = !cens || (WITH_GRAD && !eq);
+    float nll_au = 0.f, nll_mu = 0.f, nll_ac = 0.f, nll_mc = 0.f;
+    if (need_u) {
+        const float ln_sa = o.lsa0 + 0.5f * logf(sar2);    // ln s_a (true scale)
+        nll_au = 0.5f * za * za + ln_sa;                                // :14-19
+        const float dm = o.ly - lf - m_m;
+        nll_mu = 0.5f * dm * dm / sm2_ + 0.5f * logf(sm2_);             // :22-33
+    }
+    if (need_c) {
+        nll_ac = nan_to_num(-log_ndtr_f(za));                           // :574-585 with y in the omega slot (:1212)
+        const float zmc = (o.lw - lf - m_m) / s_m;
+        nll_mc = nan_to_num(-log_ndtr_f(zmc));                          // :604-616
+    }
     const float val = lam * (cens ? nll_ac : nll_au) + (1.0f - lam) * (cens ? nll_mc : nll_mu);   // :553-557
     nll = nan_to_num(val) - (o.lsa0 + o.lsm);                                                     // :559-560
     if (WITH_GRAD) {
         // all terms are coefficients of grad ln f
         const float g_sa2_over = 2.0f * cr2 / sar2;                 // grad_s_a2 / s_a2 = 2 f^2 c / s_a2
-        // gradient_cost_au :36-59, rescaled by sigma_a:  r_ = (f - y)/sigma_a = -da
-        const float g_au = 0.5f * g_sa2_over + (-da) * r * (sar2 + da * r * o.c) / (sar2 * sar2);
-        // multiplicative model :1107-1136: grad m_m = grad lnf / (1 + E) = q/(1+q) grad lnf
-        const float gmm = q / (1.0f + q);
-        const float rm = lf - m_m - o.ly;                           // sign quirk of :73,78
-        float g_mu = -gmm / sm2_;                                   // 0.5 grad_s_m2 / s_m2
-        if (!isnan(o.ly)) g_mu += 0.5f * rm / (sm2_ * sm2_) * (2.0f * sm2_ * (1.0f + gmm) + rm * 2.0f * gmm);
-        // censored branches :676-692, :709-728
-        const float ta = r - o.wr;                                  // (f + m_a - omega)/sigma_a
-        const float g_ac = norm_pdf_cdf_ratio_f(-ta / sar) * (r * sar - ta * cr2 / sar) / sar2;
-        const float tm = lf + m_m - o.lw;
-        const float g_mc = norm_pdf_cdf_ratio_f(-tm / s_m) * ((1.0f + gmm) * s_m + tm * gmm / s_m) / sm2_;
-        const bool eq = o.flags & 2u;                               // y == omega :655
-        G = eq ? (lam * g_ac + dlam * nll_ac + (1.0f - lam) * g_mc - dlam * nll_mc)
-               : (lam * g_au + dlam * nll_au + (1.0f - lam) * g_mu - dlam * nll_mu);
+        const float gmm = q / (1.0f + q);                           // multiplicative model :1107-1136: grad m_m = q/(1+q) grad lnf
+        if (!eq) {
+            // gradient_cost_au :36-59, rescaled by sigma_a:  r_ = (f - y)/sigma_a = -da
+            const float g_au = 0.5f * g_sa2_over + (-da) * r * (sar2 + da * r * o.c) / (sar2 * sar2);
+            const float rm = lf - m_m - o.ly;                       // sign quirk of :73,78
+            float g_mu = -gmm / sm2_;                               // 0.5 grad_s_m2 / s_m2
+            if (!isnan(o.ly)) g_mu += 0.5f * rm / (sm2_ * sm2_) * (2.0f * sm2_ * (1.0f + gmm) + rm * 2.0f * gmm);
+            G = lam * g_au + dlam * nll_au + (1.0f - lam) * g_mu - dlam * nll_mu;
+        } else {
+            // censored branches :676-692, :709-728 (selected by y == omega :655)
+            const float ta = r - o.wr;                              // (f + m_a - omega)/sigma_a
+            const float g_ac = norm_pdf_cdf_ratio_f(-ta / sar) * (r * sar - ta * cr2 / sar) / sar2;
+            const float tm = lf + m_m - o.lw;
+            const float g_mc = norm_pdf_cdf_ratio_f(-tm / s_m) * ((1.0f + gmm) * s_m + tm * gmm / s_m) / sm2_;
+            G = lam * g_ac + dlam * nll_ac + (1.0f - lam) * g_mc - dlam * nll_mc;
+        }
     }
 }
