@@ -61,6 +61,13 @@ SIGNATURES = {
     "bt_model_check_reset": (C.c_int, [C.c_void_p]),
     "bt_model_check_update": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, c_float_p, c_float_p]),
     "bt_model_check_get": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_int]),
+    "bt_spatial_prior_unweighted": (C.c_int, [C.c_void_p, c_uint8_p, c_double_p]),
+    "bt_chain_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bt_chain_push": (C.c_int, [C.c_void_p]),
+    "bt_chain_length": (C.c_int64, [C.c_void_p]),
+    "bt_chain_get": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_double_p]),
+    "bt_chain_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, c_double_p, c_double_p, c_double_p,
+                                 c_double_p, c_double_p, c_double_p]),
     "bt_mlp_kernel_variant": (C.c_int, [C.c_void_p]),
     "bt_kernel_launches": (C.c_int64, [C.c_void_p]),
     "bt_mlp_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int64_p, c_int64_p]),

@@ -14,6 +14,7 @@
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
 #include "mlp_tc3.cuh"
+#include "chain_kernels.cuh"
 
 static thread_local std::string g_err;
 static int fail(const char* what, const char* file, int line, cudaError_t e = cudaSuccess) {
@@ -58,6 +59,9 @@ struct bt_ctx {
     // online model checking accumulators (my_sampler.py:385-401)
     float *mc_clppd = nullptr, *mc_pvy = nullptr, *mc_pvl = nullptr;
     double mc_count = 0;
+    // on-device chain store (chain_kernels.cuh)
+    float* chain = nullptr;
+    int64_t chain_cap = 0, chain_len = 0;
     // scratch (grown on demand)
     float *rows = nullptr, *lf_rows = nullptr, *jac_rows = nullptr, *nl = nullptr, *logq = nullptr, *objc = nullptr;
     size_t rows_cap = 0, jac_cap = 0;
@@ -142,7 +146,7 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
     tc3_free(c->tc3);
     void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
-                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl};
+                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl, c->chain};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -522,6 +526,27 @@ extern "C" int bt_objective_terms(bt_ctx* c, const uint8_t* owned, double* out) 
     return 0;
 }
 
+// SpatialPrior.neglog_pdf(Theta, idx_pix = all pixels, with_weights=False) (l22_discrete_grad_prior.py:95-128): the potential
+// g(Theta) of the regularisation-weight update (abstract_sampler.py:172-210), per dimension, global convention (factor 1/2).
+extern "C" int bt_spatial_prior_unweighted(bt_ctx* c, const uint8_t* owned, double* out) {
+    READY(c);
+    REQUIRE(out, "null out");
+    REQUIRE(c->pr.has_spatial, "the posterior has no spatial prior");
+    CK(cudaSetDevice(c->device));
+    const uint8_t* od;
+    if (upload_owned(c, owned, &od)) return -1;
+    PriorDev unit = c->pr;
+    unit.has_indicator = 0;
+    for (int d = 0; d < BT_MAX_D; ++d) unit.tau[d] = 1.f;
+    CK(cudaMemsetAsync(c->tmpd, 0, 64 * sizeof(double), c->stream));
+    objective_terms_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(unit, c->N, c->D, c->max_degree, c->theta, c->nbr,
+                                                                       c->nll_lik, od, c->tmpd);
+    KLAUNCH(c);
+    CK(cudaMemcpyAsync(out, c->tmpd + 1, c->D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 extern "C" int bt_forward_map(bt_ctx* c, int M, const double* theta, double* log_f, double* grad_log_f) {
     REQUIRE(c && c->have_net && c->have_fm, "upload the network and forward map first");
     REQUIRE(M > 0 && theta && log_f, "bad arguments");
@@ -753,4 +778,103 @@ extern "C" int bt_model_check_get(bt_ctx* c, double* clppd, double* pval_y, doub
     }
     if (pval_llh && d2h_to_double(c, pval_llh, c->mc_pvl, c->N)) return -1;
     return 0;
+}
+
+// ---- on-device chain store and posterior summaries ---------------------------------------------------
+extern "C" int bt_chain_reserve(bt_ctx* c, int64_t capacity) {
+    REQUIRE(c, "null ctx");
+    REQUIRE(capacity >= 0, "negative capacity");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->chain) { cudaFree(c->chain); c->chain = nullptr; }
+    c->chain_cap = 0; c->chain_len = 0;
+    if (capacity > 0) {
+        CK(cudaMalloc(&c->chain, (size_t)capacity * c->N * c->D * sizeof(float)));
+        c->chain_cap = capacity;
+    }
+    return 0;
+}
+
+extern "C" int bt_chain_push(bt_ctx* c) {
+    REQUIRE(c && c->chain, "no chain reserved");
+    REQUIRE(c->chain_len < c->chain_cap, "chain store is full");
+    CK(cudaSetDevice(c->device));
+    const size_t nd = (size_t)c->N * c->D;
+    CK(cudaMemcpyAsync(c->chain + (size_t)c->chain_len * nd, c->theta, nd * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    c->chain_len++;
+    return 0;
+}
+
+extern "C" int64_t bt_chain_length(bt_ctx* c) { return c ? c->chain_len : -1; }
+
+extern "C" int bt_chain_get(bt_ctx* c, int64_t first, int64_t count, double* out) {
+    REQUIRE(c && c->chain && out, "bad arguments");
+    REQUIRE(first >= 0 && count >= 0 && first + count <= c->chain_len, "iterate range outside the stored chain");
+    CK(cudaSetDevice(c->device));
+    const size_t nd = (size_t)c->N * c->D;
+    for (int64_t t = 0; t < count; ++t)
+        if (d2h_to_double(c, out + (size_t)t * nd, c->chain + (size_t)(first + t) * nd, nd)) return -1;
+    return 0;
+}
+
+extern "C" int bt_chain_stats(bt_ctx* c, int64_t first, int64_t count, int n_q, const double* percentiles, double* mean,
+                              double* var, double* q_lo, double* q_hi, double* q_frac) {
+    REQUIRE(c && c->chain, "no chain reserved");
+    REQUIRE(first >= 0 && count >= 1 && first + count <= c->chain_len, "iterate range outside the stored chain");
+    REQUIRE(count < (int64_t)1 << 30, "chain too long");
+    REQUIRE(n_q >= 0 && n_q <= BT_CHAIN_MAX_Q, "too many percentiles");
+    REQUIRE(n_q == 0 || (percentiles && q_lo && q_hi && q_frac), "null percentile arguments");
+    CK(cudaSetDevice(c->device));
+    const int T = (int)count;
+    ChainRanks rk{};
+    rk.n = n_q;
+    for (int q = 0; q < n_q; ++q) {
+        REQUIRE(percentiles[q] >= 0.0 && percentiles[q] <= 100.0, "percentile outside [0, 100]");
+        const double pos = percentiles[q] / 100.0 * (double)(T - 1);     // numpy 'linear': virtual index
+        int lo = (int)floor(pos);
+        if (lo > T - 1) lo = T - 1;
+        rk.lo[q] = lo;
+        rk.hi[q] = lo + 1 < T ? lo + 1 : T - 1;
+        q_frac[q] = pos - (double)lo;
+    }
+    const size_t nd = (size_t)c->N * c->D;
+    float* outbuf = nullptr;                                             // mean | var | lo[n_q] | hi[n_q]
+    CK(cudaMalloc(&outbuf, (size_t)(2 + 2 * n_q) * nd * sizeof(float)));
+    float *d_mean = outbuf, *d_var = outbuf + nd, *d_lo = outbuf + 2 * nd, *d_hi = outbuf + (size_t)(2 + n_q) * nd;
+    // threads per block: the widest tile [T][tpb] float32 that fits 200 KB of shared memory
+    int tpb = 0;
+    for (int cand = 128; cand >= 32; cand >>= 1)
+        if ((size_t)T * cand * sizeof(float) <= 200 * 1024) { tpb = cand; break; }
+    int rc = 0;
+    if (tpb) {
+        const size_t smem = (size_t)T * tpb * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(chain_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaFree(outbuf); return fail("cudaFuncSetAttribute", __FILE__, __LINE__, e); }
+        chain_stats_kernel<true><<<(unsigned)((nd + tpb - 1) / tpb), tpb, smem, c->stream>>>(c->chain, nd, first, T, rk, 0, nd,
+            nullptr, 0, d_mean, var ? d_var : nullptr, d_lo, d_hi);
+        c->launches++;
+    } else {
+        // long chains: sort in a global scratch tile [T][chunk], chunk series per launch
+        const size_t chunk = nd < 65536 ? nd : 65536;
+        float* scratch = nullptr;
+        cudaError_t e = cudaMalloc(&scratch, (size_t)T * chunk * sizeof(float));
+        if (e != cudaSuccess) { cudaFree(outbuf); return fail("cudaMalloc(chain scratch)", __FILE__, __LINE__, e); }
+        for (size_t s0 = 0; s0 < nd; s0 += chunk) {
+            const size_t ns = nd - s0 < chunk ? nd - s0 : chunk;
+            chain_stats_kernel<false><<<(unsigned)((ns + 127) / 128), 128, 0, c->stream>>>(c->chain, nd, first, T, rk, s0, ns,
+                scratch, chunk, d_mean, var ? d_var : nullptr, d_lo, d_hi);
+            c->launches++;
+        }
+        cudaStreamSynchronize(c->stream);
+        cudaFree(scratch);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail("chain_stats_kernel", __FILE__, __LINE__, e);
+    if (!rc && mean) rc = d2h_to_double(c, mean, d_mean, nd);
+    if (!rc && var) rc = d2h_to_double(c, var, d_var, nd);
+    if (!rc && n_q) rc = d2h_to_double(c, q_lo, d_lo, (size_t)n_q * nd);
+    if (!rc && n_q) rc = d2h_to_double(c, q_hi, d_hi, (size_t)n_q * nd);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(outbuf);
+    return rc;
 }

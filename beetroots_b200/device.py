@@ -231,6 +231,46 @@ class DevicePosterior:
         return {"nll": np.float64(out[0]), "nl_prior_spatial": out[1:1 + D].copy(),
                 "nl_prior_indicator": out[1 + D:1 + 2 * D].copy(), "objective": float(out[1 + 2 * D])}
 
+    def spatial_prior_unweighted(self, owned=None) -> np.ndarray:
+        """prior_spatial.neglog_pdf(Theta, idx_pix=arange(N), with_weights=False) -> (D,)
+        (l22_discrete_grad_prior.py:95-128), at the resident Theta."""
+        out = np.zeros(self.D)
+        ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+        L.check(self._lib.bt_spatial_prior_unweighted(self._ctx, L.dptr(ow, C.c_uint8), L.dptr(out)),
+                "bt_spatial_prior_unweighted")
+        return out
+
+    # ------------------------------------------------------------------ on-device chain store (SURVEY §8f rank 1)
+    def chain_reserve(self, capacity: int):
+        L.check(self._lib.bt_chain_reserve(self._ctx, int(capacity)), "bt_chain_reserve")
+
+    def chain_push(self):
+        L.check(self._lib.bt_chain_push(self._ctx), "bt_chain_push")
+
+    def chain_length(self) -> int:
+        return int(self._lib.bt_chain_length(self._ctx))
+
+    def chain_get(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Stored iterates [first, first + count) as (count, N, D) float64 -- the saver's ``list_Theta``."""
+        count = self.chain_length() - first if count is None else count
+        out = np.empty((count, self.N, self.D))
+        L.check(self._lib.bt_chain_get(self._ctx, first, count, L.dptr(out)), "bt_chain_get")
+        return out
+
+    def chain_stats(self, first: int = 0, count: Optional[int] = None, percentiles=(), want_var: bool = False) -> dict:
+        """Per (pixel, parameter) summaries of the stored chain, computed on the device: ``mean`` (N, D) in scaled space
+        and, per percentile, the bracketing order statistics ``lo`` / ``hi`` (n_q, N, D) with weight ``frac`` (n_q)."""
+        count = self.chain_length() - first if count is None else count
+        q = L.as_f64(np.asarray(percentiles, dtype=np.float64).reshape(-1))
+        nq = q.size
+        mean = np.empty((self.N, self.D))
+        var = np.empty((self.N, self.D)) if want_var else None
+        lo, hi, frac = np.empty((nq, self.N, self.D)), np.empty((nq, self.N, self.D)), np.empty(nq)
+        L.check(self._lib.bt_chain_stats(self._ctx, first, count, nq, L.dptr(q) if nq else None, L.dptr(mean), L.dptr(var),
+                                         L.dptr(lo) if nq else None, L.dptr(hi) if nq else None,
+                                         L.dptr(frac) if nq else None), "bt_chain_stats")
+        return {"mean": mean, "var": var, "percentiles": q, "lo": lo, "hi": hi, "frac": frac, "count": count}
+
     def forward_map(self, Theta: np.ndarray, compute_derivatives: bool = False) -> dict:
         """ForwardMap.compute_all on arbitrary rows (neural_network_approx.py:152-305)."""
         Theta = L.as_f64(Theta)

@@ -205,6 +205,37 @@ class ShardedDevicePosterior:
         return {"nll": np.float64(vec[0]), "nl_prior_spatial": vec[1:1 + D], "nl_prior_indicator": vec[1 + D:1 + 2 * D],
                 "objective": float(vec[-1])}
 
+    def spatial_prior_unweighted(self):
+        return self._allreduce(self.local.spatial_prior_unweighted(self._owned))
+
+    def update_spatial_weights(self, ps, pi):
+        self.local.update_spatial_weights(ps, pi)
+
+    # the chain store is per band; summaries are gathered like any other per-pixel array
+    def chain_reserve(self, capacity):
+        self.local.chain_reserve(capacity)
+
+    def chain_push(self):
+        self.local.chain_push()
+
+    def chain_length(self):
+        return self.local.chain_length()
+
+    def chain_get(self, first=0, count=None):
+        loc = self.local.chain_get(first, count)                         # (T, N_loc, D)
+        return np.swapaxes(self._gather_owned(np.ascontiguousarray(np.swapaxes(loc, 0, 1))), 0, 1) if self.world > 1 else loc
+
+    def chain_stats(self, first=0, count=None, percentiles=(), want_var=False):
+        st = self.local.chain_stats(first, count, percentiles, want_var)
+        if self.world == 1:
+            return st
+        for k in ("mean", "var"):
+            if st[k] is not None:
+                st[k] = self._gather_owned(st[k])
+        for k in ("lo", "hi"):
+            st[k] = np.swapaxes(self._gather_owned(np.ascontiguousarray(np.swapaxes(st[k], 0, 1))), 0, 1)
+        return st
+
     def _allreduce(self, arr):
         if self.world == 1:
             return arr

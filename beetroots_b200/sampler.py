@@ -20,6 +20,7 @@ from typing import List, Optional, Union
 import numpy as np
 
 from .device import MLP_FP32, DevicePosterior
+from .mml import EBayesMMLELogRate
 
 
 class MySamplerParams:
@@ -52,7 +53,8 @@ class MySamplerParams:
 
 class B200Sampler:
     def __init__(self, my_sampler_params, D: int, L: int, N: int,
-                 rng: np.random.Generator = None, device: int = 0, mlp_mode: int = MLP_FP32):
+                 rng: np.random.Generator = None, device: int = 0, mlp_mode: int = MLP_FP32,
+                 device_chain: int = 0, device_chain_thin: int = 1):
         p = my_sampler_params
         self.eps0 = p.initial_step_size
         self.lambda_ = p.extreme_grad
@@ -77,6 +79,11 @@ class B200Sampler:
         self.j_t = np.zeros((N * D,))
         self.current = {}
         self.philox_seed = None
+        # on-device chain store: keep up to ``device_chain`` post-burn-in iterates (every
+        # ``device_chain_thin``-th) in HBM and summarise them there, see posterior_summary()
+        assert device_chain >= 0 and device_chain_thin >= 1
+        self.device_chain = int(device_chain)
+        self.device_chain_thin = int(device_chain_thin)
         self._dev: Optional[DevicePosterior] = None
         self._dev_owner = None
 
@@ -156,14 +163,40 @@ class B200Sampler:
         acc, lpa = dev.reduce_step_stats()
         return acc / self.N, lpa / self.N
 
+    def sample_regu_hyperparams(self, posterior, regu_weights_optimizer, t: int, current_Theta=None) -> np.ndarray:
+        """sampler/abstract_sampler.py:172-210; the potential is reduced on the device at the resident Theta
+        (``current_Theta`` is accepted for signature compatibility and ignored)."""
+        assert self.N > 1
+        assert posterior.prior_spatial is not None
+        dev = self.attach(posterior)
+        tau_tm1 = np.asarray(posterior.prior_spatial.weights, dtype=np.float64) * 1
+        neglog_prior = dev.spatial_prior_unweighted()                              # (D,)
+        new_tau = regu_weights_optimizer.update(tau_tm1.mean(), t, neglog_prior.sum())
+        return new_tau * np.ones((self.D,))
+
+    def posterior_summary(self, list_CI=(68, 90, 95, 99), from_scaled_to_lin=None, first: int = 0,
+                          count: Optional[int] = None) -> dict:
+        """MMSE and credibility intervals of the chain kept on the device, as the reference's results extraction
+        computes them from the HDF5 file (inversion/results/utils/mc.py:190-215): mean in scaled space (mapped to
+        linear space if ``from_scaled_to_lin`` is given), ``np.percentile`` (linear interpolation) of the chain in
+        linear space for the lower / upper percentile of every credibility level.  Keys follow the reference's csv
+        columns (``Theta_MMSE``, ``per_2p5`` ...)."""
+        assert self._dev is not None and self.device_chain, "no chain was kept on the device"
+        per = sorted({(100 - ci) / 2 for ci in list_CI} | {100 - (100 - ci) / 2 for ci in list_CI})
+        st = self._dev.chain_stats(first, count, per)
+        f = (lambda a: a) if from_scaled_to_lin is None else (lambda a: from_scaled_to_lin(a.reshape(-1, self.D)).reshape(a.shape))
+        out = {"Theta_MMSE_scaled": st["mean"], "Theta_MMSE": f(st["mean"]), "count": st["count"]}
+        for q, p in enumerate(per):
+            lo, hi, g = f(st["lo"][q]), f(st["hi"][q]), st["frac"][q]
+            out[f"per_{p:.1f}".replace(".", "p")] = lo + g * (hi - lo)
+        return out
+
     # ------------------------------------------------------------------ main loop
     def sample(self, posterior, saver, max_iter: int, Theta_0: Optional[np.ndarray] = None,
                disable_progress_bar: bool = False, regu_spatial_N0: Union[int, float] = np.inf,
                regu_spatial_scale: float = 1.0, regu_spatial_vmin: float = 1e-8, regu_spatial_vmax: float = 1e8,
                T_BI: int = 0) -> None:
         """sampler/my_sampler.py:269-559."""
-        if regu_spatial_N0 < np.inf:
-            raise NotImplementedError("regularisation-weight optimisation is not on the GPU path yet (SURVEY.md §8f rank 3)")
         additional_sampling_log = {}
         if Theta_0 is None:
             print("starting from a random point")
@@ -182,6 +215,12 @@ class B200Sampler:
         assert np.sum(np.isinf(self.v)) == 0.0
         self.j_t = np.zeros((self.N * self.D,))
         dev.model_check_reset()                                                    # :385-401
+        regu_weights_optimizer = EBayesMMLELogRate(scale=regu_spatial_scale, N0=regu_spatial_N0, N1=+np.inf,
+                                                   dim=self.D * self.N, vmin=regu_spatial_vmin, vmax=regu_spatial_vmax,
+                                                   homogeneity=2.0, exponent=0.8)           # :369-379
+        optimize_regu_weights = regu_weights_optimizer.N0 < np.inf
+        if self.device_chain:
+            dev.chain_reserve(self.device_chain)
 
         try:
             from tqdm.auto import tqdm
@@ -189,6 +228,14 @@ class B200Sampler:
         except Exception:                                                          # pragma: no cover
             it = range(1, max_iter + 1)
         for t in it:
+            if optimize_regu_weights and (self.N > 1):                              # :403-427
+                assert posterior.prior_spatial is not None
+                if t >= regu_weights_optimizer.N0:
+                    tau_t = self.sample_regu_hyperparams(posterior, regu_weights_optimizer, t)
+                    posterior.prior_spatial.weights = tau_t * 1
+                    # the device assembles prior terms from the resident Theta on the fly: nothing to recompute (:419-425)
+                    dev.update_spatial_weights(posterior.prior_spatial, posterior.prior_indicator)
+                additional_sampling_log["tau"] = posterior.prior_spatial.weights * 1
             type_t = int(np.argmax(self.rng.multinomial(1, pvals=self.selection_probas)))   # :430-435
             if type_t == 0:
                 accepted_t, log_proba_accept_t = self.generate_new_sample_mtm(t, posterior)
@@ -215,6 +262,9 @@ class B200Sampler:
                 saver.update_memory(t, rng_state_array=rng_state_array, rng_inc_array=rng_inc_array, **kw)
             if saver.check_need_to_save(t):                                        # :539-541
                 saver.save_to_file()
+            if (self.device_chain and t > T_BI and t % self.device_chain_thin == 0
+                    and dev.chain_length() < self.device_chain):
+                dev.chain_push()
         self._pull_state(with_current=True)
         clppd, p_values_y, p_values_llh = dev.model_check_get(finalize=True)       # :544-549
         saver.save_additional(list_arrays=[clppd, p_values_y, p_values_llh],

@@ -108,6 +108,12 @@ int bt_get_current(bt_ctx* ctx, double* log_f, double* nll_pix, double* grad_lik
  * out[1+2D] = objective.  Sums run over pixels flagged in owned (N uint8) or all if NULL. */
 int bt_objective_terms(bt_ctx* ctx, const uint8_t* owned, double* out);
 
+/* SpatialPrior.neglog_pdf(Theta, idx_pix = all pixels, with_weights=False)
+ * (modelling/priors/l22_discrete_grad_prior.py:95-128): out[d] = 1/2 sum_n sum_{i in V_n} (Theta_nd - Theta_id)^2, d < D --
+ * the potential g(Theta) of the regularisation-weight update, Sampler.sample_regu_hyperparams
+ * (sampler/abstract_sampler.py:172-210).  Pixels flagged in owned (N uint8), or all if NULL. */
+int bt_spatial_prior_unweighted(bt_ctx* ctx, const uint8_t* owned, double* out);
+
 /* ForwardMap.compute_all on arbitrary rows (neural_network_approx.py:152-305): theta (M, D)
  * host -> log_f (M, L), grad_log_f (M, D, L) or NULL. */
 int bt_forward_map(bt_ctx* ctx, int M, const double* theta, double* log_f, double* grad_log_f);
@@ -154,6 +160,26 @@ int bt_debug_philox_mtm(bt_ctx* ctx, int site, int K, uint64_t seed, int64_t t, 
 int bt_model_check_reset(bt_ctx* ctx);
 int bt_model_check_update(bt_ctx* ctx, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject);
 int bt_model_check_get(bt_ctx* ctx, double* clppd, double* pval_y, double* pval_llh, int finalize);
+
+/* ---- on-device chain store and posterior summaries ------------------------------------------------------
+ * Replaces the round trip saver memory -> HDF5 `list_Theta` (sampler/saver/my_saver.py:46-83, abstract_saver.py:190-213)
+ * -> per-pixel re-read + np.mean / np.percentile (inversion/results/utils/mc.py:158-215): the (thinned) chain stays in
+ * HBM as [T][N][D] float32 and is summarised there.
+ *   bt_chain_reserve   allocate room for `capacity` iterates (drops a previous chain; 0 frees it)
+ *   bt_chain_push      append the resident Theta (device-to-device, asynchronous on the context's stream)
+ *   bt_chain_get       iterates [first, first + count) as HOST double (count, N, D) -- what update_memory stores
+ *   bt_chain_stats     over iterates [first, first + count), per (pixel, parameter): mean (N, D) and population variance
+ *                      (N, D) in scaled space (either may be NULL), and for each of the n_q <= 16 percentiles p (in
+ *                      [0, 100]) the two order statistics that bracket numpy's 'linear' virtual index p/100 (count-1):
+ *                      q_lo, q_hi (n_q, N, D) and the interpolation weight q_frac (n_q), so that the caller can
+ *                      interpolate after mapping to linear space exactly as the reference does
+ *                      (percentile = lo + frac (hi - lo)). */
+int bt_chain_reserve(bt_ctx* ctx, int64_t capacity);
+int bt_chain_push(bt_ctx* ctx);
+int64_t bt_chain_length(bt_ctx* ctx);
+int bt_chain_get(bt_ctx* ctx, int64_t first, int64_t count, double* out);
+int bt_chain_stats(bt_ctx* ctx, int64_t first, int64_t count, int n_q, const double* percentiles, double* mean,
+                   double* var, double* q_lo, double* q_hi, double* q_frac);
 
 /* which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 3 = pair kernel (default),
  * 1 = single-CTA kernel (fallback for shapes the pair kernel does not take), 2 = first cta_group::2 kernel, 0 = none. */

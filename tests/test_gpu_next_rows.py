@@ -1,0 +1,181 @@
+"""GPU: the SURVEY §8f "next" rows built on top of the sampler step -- on-device chain store + posterior summaries
+(rank 1) and the regularisation-weight update (rank 3) -- through the C ABI, against numpy / the oracle / reference
+goldens.  Order statistics and stored iterates are bit-exact (float32 moves, no arithmetic); means and the spatial
+potential are float32 sums compared at rtol 1e-6 / 1e-5."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from _cases import GOLDEN, load_golden, problem_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from beetroots_b200 import _lib
+    return _lib.load()
+
+
+def _synthetic(H, W, K, nnn=False):
+    from beetroots_b200.synthetic import make_problem
+    from oracle import posterior as OP
+    return make_problem(H, W, lambda fm, th: OP.forward_map_compute_all(fm, th, False)["log_f_Theta"], L=10, k_mtm=K,
+                        use_next_nearest_neighbors=nnn)
+
+
+def _np_percentile_from_brackets(st):
+    return st["lo"] + st["frac"][:, None, None] * (st["hi"] - st["lo"])
+
+
+@pytest.mark.parametrize("T,N", [(1, 7), (2, 33), (37, 300), (401, 130), (900, 70), (1700, 40), (2500, 33)])
+def test_chain_store_and_summaries_vs_numpy(lib, T, N):
+    """Synthetic iterates pushed through bt_set_state / bt_chain_push: stored chain bit-identical to what was pushed;
+    mean / variance / percentiles equal numpy's on the same float32 chain (all three shared-memory tile widths and the
+    global-scratch path for long chains; ties, constants and single-iterate chains included)."""
+    from beetroots_b200 import DevicePosterior
+    prob = _synthetic(1, N, 4) if N < 64 else _synthetic(N // 10, 10, 4)
+    post = prob.posterior
+    rng = np.random.default_rng(T * 1000 + N)
+    dev = DevicePosterior.from_posterior(post)
+    try:
+        dev.chain_reserve(T + 3)
+        chain = rng.standard_normal((T + 3, post.N, post.D)).astype(np.float32)
+        chain[:, 0, :] = 1.25                                        # constant series
+        chain[:, 1, 0] = np.round(chain[:, 1, 0])                    # many ties
+        if T > 2:
+            chain[:, 2, 1] = np.sort(chain[:, 2, 1])[::-1]           # already sorted, descending
+        for t in range(T + 3):
+            dev.set_state(chain[t].astype(np.float64))
+            dev.chain_push()
+        assert dev.chain_length() == T + 3
+        with pytest.raises(Exception, match="full"):
+            dev.chain_push()
+        got = dev.chain_get()
+        assert np.array_equal(got, chain.astype(np.float64))
+        per = [0.5, 2.5, 5, 16, 50, 84, 95, 97.5, 99.5, 0, 100]
+        first = 2                                                    # burn-in of two stored iterates
+        st = dev.chain_stats(first, T, per, want_var=True)
+        ref = chain[first:first + T].astype(np.float64)
+        np.testing.assert_allclose(st["mean"], ref.mean(axis=0), rtol=0, atol=2e-7 * (1 + np.abs(ref).max()))
+        np.testing.assert_allclose(st["var"], ref.var(axis=0), rtol=2e-6, atol=1e-7)
+        srt = np.sort(ref, axis=0)
+        pos = np.array(per) / 100 * (T - 1)
+        lo = np.floor(pos).astype(int)
+        hi = np.minimum(lo + 1, T - 1)
+        assert np.array_equal(st["lo"], srt[lo]) and np.array_equal(st["hi"], srt[hi])       # exact order statistics
+        np.testing.assert_allclose(st["frac"], pos - lo, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(_np_percentile_from_brackets(st), np.percentile(ref, per, axis=0), rtol=1e-12, atol=1e-12)
+        with pytest.raises(Exception, match="outside the stored chain"):
+            dev.chain_stats(first, T + 2, per)
+        dev.chain_reserve(0)
+        with pytest.raises(Exception, match="no chain"):
+            dev.chain_push()
+    finally:
+        dev.close()
+
+
+@pytest.mark.parametrize("name", ["ref_n4_6x5", "ref_n8_5x6_censored"])
+def test_spatial_potential_vs_reference_golden(lib, name):
+    """bt_spatial_prior_unweighted at the golden states == reference L22 neglog_pdf(with_weights=False)
+    (tests/golden/mml_golden.json, made by make_golden_mml.py)."""
+    from beetroots_b200 import DevicePosterior
+    with open(os.path.join(GOLDEN, "mml_golden.json")) as f:
+        ref = json.load(f)[f"{name}|scale=1.0|N0=1"]["gX_per_dim"]
+    g = load_golden(name)
+    post, _ = problem_from_golden(g)
+    states = [g["theta0"]] + [g[f"t{t}_Theta"] for t in range(1, len(g["kernels"]) + 1)]
+    dev = DevicePosterior.from_posterior(post)
+    try:
+        for th, r in zip(states, ref):
+            dev.set_state(th)
+            np.testing.assert_allclose(dev.spatial_prior_unweighted(), r, rtol=1e-5)
+            # weights do not enter, whatever they are
+            post.prior_spatial.weights = post.prior_spatial.weights * 3.0
+            dev.update_spatial_weights(post.prior_spatial, post.prior_indicator)
+            np.testing.assert_allclose(dev.spatial_prior_unweighted(), r, rtol=1e-5)
+    finally:
+        dev.close()
+
+
+class _MemSaver:
+    def __init__(self):
+        self.memory, self.tau, self.Theta, self.additional = {}, [], [], None
+
+    def initialize_memory(self, T_MC, t, **kw):
+        self.memory = {"started": True}
+
+    def update_memory(self, t, Theta, additional_sampling_log, **kw):
+        self.Theta.append(Theta.copy())
+        self.tau.append(np.array(additional_sampling_log["tau"]))
+
+    def check_need_to_update_memory(self, t):
+        return True
+
+    def check_need_to_save(self, t):
+        return False
+
+    def save_to_file(self):
+        pass
+
+    def save_additional(self, list_arrays, list_names):
+        self.additional = dict(zip(list_names, list_arrays))
+
+
+def test_sample_with_regu_weight_update_and_device_chain(lib):
+    """``sample(..., regu_spatial_N0=3)``: the logged tau follows the reference recursion (mirror optimiser fed with the
+    float64 oracle potential of the saved iterates), prior_spatial.weights is updated in place like the reference
+    does, the step keeps using the new weights (objective terms agree with the oracle at the final tau); the chain
+    kept on the device equals the iterates handed to the saver and its summaries equal numpy's."""
+    from beetroots_b200 import B200Sampler, MySamplerParams
+    from beetroots_b200.mml import EBayesMMLELogRate
+    from beetroots_b200.modelling import build_neighbor_table
+    from oracle import posterior as OP
+    prob = _synthetic(12, 9, 5)
+    post = prob.posterior
+    nbr = build_neighbor_table(post.prior_spatial.list_edges, post.N, 4)
+    tau0 = post.prior_spatial.weights.copy()
+    T, N0, T_BI = 14, 3, 4
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], 5, True, False), post.D, post.L, post.N,
+                      rng=np.random.default_rng(11), device_chain=T, device_chain_thin=2)
+    sv = _MemSaver()
+    smp.sample(post, sv, T, Theta_0=prob.theta_init, disable_progress_bar=True, regu_spatial_N0=N0,
+               regu_spatial_scale=1.0, T_BI=T_BI)
+    assert len(sv.tau) == T
+    opt = EBayesMMLELogRate(scale=1.0, N0=N0, N1=+np.inf, dim=post.D * post.N, vmin=1e-8, vmax=1e8, homogeneity=2.0,
+                            exponent=0.8)
+    tau = float(tau0.mean())
+    prev = prob.theta_init
+    for t in range(1, T + 1):
+        if t >= N0:
+            had, _ = OP.spatial_sums(prev, nbr)
+            tau = opt.update(tau, t, float(0.5 * had.sum()))
+            expect = tau * np.ones(post.D)
+        else:
+            expect = tau0
+        np.testing.assert_allclose(sv.tau[t - 1], expect, rtol=1e-4)
+        prev = sv.Theta[t - 1]
+    assert np.abs(sv.tau[-1] - tau0).max() > 1e-3 * tau0.max(), "tau did not move: the test would be vacuous"
+    np.testing.assert_allclose(post.prior_spatial.weights, sv.tau[-1], rtol=0, atol=0)
+    # the device keeps sampling with the updated weights
+    cur = OP.compute_all(post, sv.Theta[-1], nbr)
+    dobj = smp._dev.objective_terms()
+    np.testing.assert_allclose(dobj["nl_prior_spatial"].sum(), (cur["objective_pix_global"] - cur["nll_pix"]
+                               - OP.indicator_penalty(sv.Theta[-1], post.prior_indicator)).sum(), rtol=1e-4)
+    # on-device chain: iterates t = 6, 8, ..., 14 (t > T_BI, every second one)
+    kept = [t for t in range(1, T + 1) if t > T_BI and t % 2 == 0]
+    chain = smp._dev.chain_get()
+    assert chain.shape[0] == len(kept)
+    for k, t in enumerate(kept):
+        np.testing.assert_allclose(chain[k], sv.Theta[t - 1], rtol=0, atol=0)
+    summ = smp.posterior_summary(list_CI=[68, 95], from_scaled_to_lin=lambda a: 10.0 ** a)
+    lin = 10.0 ** chain
+    np.testing.assert_allclose(summ["Theta_MMSE_scaled"], chain.mean(axis=0), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(summ["Theta_MMSE"], 10.0 ** summ["Theta_MMSE_scaled"], rtol=1e-12)
+    assert set(summ) == {"Theta_MMSE_scaled", "Theta_MMSE", "count", "per_2p5", "per_16p0", "per_84p0", "per_97p5"}
+    for key, p in (("per_2p5", 2.5), ("per_16p0", 16.0), ("per_84p0", 84.0), ("per_97p5", 97.5)):
+        np.testing.assert_allclose(summ[key], np.percentile(lin, p, axis=0), rtol=1e-12)

@@ -1,9 +1,11 @@
 """CPU: the oracle port against (1) the golden vectors recorded from the UNMODIFIED reference
 (tests/golden/make_golden.py) and (2) the reference's own known-answer tests for this path."""
+import os
+
 import numpy as np
 import pytest
 
-from _cases import GOLDEN_CASES, golden_noise, load_golden, problem_from_golden
+from _cases import GOLDEN, GOLDEN_CASES, golden_noise, load_golden, problem_from_golden
 from oracle import posterior as OP
 from oracle.sampler import OracleSampler
 
@@ -120,3 +122,34 @@ def test_model_check_matches_reference(name):
     c, py, pl = orc.model_check_get()
     assert rel(c, g["mc_clppd"]) < 1e-8
     assert np.mean(py != g["mc_pval_y"]) < 0.01 and np.mean(pl != g["mc_pval_llh"]) < 0.05   # za/zm reproduce y_rep to 1 ulp
+
+
+# ---- regularisation-weight update: optimiser mirror and spatial potential vs the reference ----
+def _mml_golden():
+    import json
+    with open(os.path.join(GOLDEN, "mml_golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("key", sorted(_mml_golden().keys()))
+def test_regu_weight_optimiser_and_potential_vs_reference_golden(key):
+    """tests/golden/make_golden_mml.py ran the reference's EBayesMMLELogRate / L22 prior; the host mirror
+    (beetroots_b200/mml.py) and the oracle's neighbour sums must reproduce both."""
+    from beetroots_b200.mml import EBayesMMLELogRate
+    ref = _mml_golden()[key]
+    name, scale, N0 = key.split("|")
+    scale, N0 = float(scale.split("=")[1]), int(N0.split("=")[1])
+    g = load_golden(name)
+    post, nbr = problem_from_golden(g)
+    states = [g["theta0"]] + [g[f"t{t}_Theta"] for t in range(1, len(g["kernels"]) + 1)]
+    opt = EBayesMMLELogRate(scale=scale, N0=N0, N1=+np.inf, dim=post.D * post.N, vmin=1e-8, vmax=1e8, homogeneity=2.0,
+                            exponent=0.8)
+    tau = float(np.mean(g["tau"]))
+    for t, th in enumerate(states, start=1):
+        had, _ = OP.spatial_sums(th, nbr)
+        gX = 0.5 * had.sum(axis=0)                                  # l22_discrete_grad_prior.py:106-128, factor 1/2
+        np.testing.assert_allclose(gX, ref["gX_per_dim"][t - 1], rtol=1e-12)
+        if t >= N0:
+            tau = opt.update(tau, t, float(gX.sum()))
+        np.testing.assert_allclose(tau, ref["tau"][t - 1], rtol=1e-12)
+        np.testing.assert_allclose(opt.mean_theta, ref["mean_theta"][t - 1], rtol=1e-12)
