@@ -625,7 +625,6 @@ extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t,
     REQUIRE(site >= 0 && site < c->n_sites, "no such site");
     REQUIRE(K >= 1, "k_mtm must be >= 1");
     REQUIRE(c->pr.has_indicator, "The Posterior has no specified smooth indicator prior");   // my_sampler.py:132-133
-    REQUIRE(c->pr.has_spatial || cand_inject, "MTM without a spatial prior needs injected proposals (not on the GPU path)");
     CK(cudaSetDevice(c->device));
     const int n_pix = c->site_size[site];
     if (n_pix == 0) return 0;

@@ -45,6 +45,7 @@ static_assert(sizeof(ObsConst) == 48, "ObsConst must be 48 bytes");
 #define BT_PURPOSE_MTM_SUBSET 4u
 #define BT_PURPOSE_MTM_USEL 5u
 #define BT_PURPOSE_MTM_UACC 6u
+#define BT_PURPOSE_MTM_IND 9u     /* 7, 8: model check (sampler_kernels.cuh) */
 
 __host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];

@@ -254,6 +254,34 @@ __global__ void pmala_accept_kernel(PriorDev pr, FmapDev fm, int n_pix, const in
 }
 
 // ---- MTM -----------------------------------------------------------------------------------
+// One draw from the smooth indicator prior of dimension d (sampler/utils/utils.py:50-97, Appendix B of the paper):
+// with probability w = Z_u / (1 + Z_u), Z_u = 2 (hi - lo) / (delta Gamma(1/4)), uniform in [lo, hi]; otherwise a
+// generalised-Gaussian tail exp(-(x/delta)^4) glued to the nearer bound (utils.py:12-47: x = +-Z^(1/4) with
+// Z ~ Gamma(1/4, delta^4)).  Gamma(1/4): G_a = G_{a+1} U^{1/a} with Marsaglia-Tsang for shape 5/4, so
+// Z^(1/4) = delta G_{5/4}^{1/4} U.  All randomness from Philox blocks (purpose MTM_IND, sub-index 16 (k D + d) + j).
+__device__ __forceinline__ float smooth_indicator_draw(const PriorDev& pr, int d, uint64_t seed, int64_t t, int site,
+                                                       int64_t gid, uint32_t sub) {
+    const float lo = pr.lo[d], hi = pr.hi[d];
+    const float zu = 2.f * (hi - lo) * pr.inv_delta * (1.0f / 3.6256099082219083f);
+    uint32_t r[4];
+    bt_philox(r, seed, t, BT_PURPOSE_MTM_IND, site, gid, sub * 16u);
+    if (u01(r[0]) * (1.f + zu) < zu) return lo + (hi - lo) * u01(r[1]);                // :83-85, :96
+    const float dd = 1.25f - 1.0f / 3.0f, cc = rsqrtf(9.f * dd);
+    float gam = dd;                                                                   // (fallback after 15 rejections: p < 1e-20)
+    for (uint32_t j = 1; j < 16u; ++j) {
+        uint32_t q[4];
+        bt_philox(q, seed, t, BT_PURPOSE_MTM_IND, site, gid, sub * 16u + j);
+        float x, x_unused;
+        box_muller(q[0], q[1], x, x_unused);
+        const float v1 = 1.f + cc * x;
+        if (v1 <= 0.f) continue;
+        const float v = v1 * v1 * v1;
+        if (logf(u01(q[2])) < 0.5f * x * x + dd - dd * v + dd * logf(v)) { gam = dd * v; break; }
+    }
+    const float mag = sqrtf(sqrtf(gam)) * u01(r[3]) / pr.inv_delta;                    // delta G^(1/4)
+    return (r[2] & 1u) ? hi + mag : lo - mag;                                         // :87-95
+}
+
 // candidate generation (sampler/utils/utils.py:274-349): thread per (pixel, k); slot K = current value
 __global__ void mtm_gen_kernel(PriorDev pr, int n_pix, const int* __restrict__ site_pix, int D, int K, int max_degree,
                                const float* __restrict__ theta, const int* __restrict__ nbr, uint64_t seed,
@@ -270,6 +298,11 @@ __global__ void mtm_gen_kernel(PriorDev pr, int n_pix, const int* __restrict__ s
     }
     if (cand_inject) {
         for (int d = 0; d < D; ++d) out[d] = cand_inject[((size_t)n * K + k) * D + d];
+        return;
+    }
+    if (!pr.has_spatial) {                                                            // my_sampler.py:135-143
+        const int64_t g0 = gid ? gid[n] : (int64_t)n;
+        for (int d = 0; d < D; ++d) out[d] = smooth_indicator_draw(pr, d, seed, t, site, g0, (uint32_t)(k * BT_MAX_D + d));
         return;
     }
     const int* nb = nbr + (size_t)n * max_degree;

@@ -179,3 +179,110 @@ def test_sample_with_regu_weight_update_and_device_chain(lib):
     assert set(summ) == {"Theta_MMSE_scaled", "Theta_MMSE", "count", "per_2p5", "per_16p0", "per_84p0", "per_97p5"}
     for key, p in (("per_2p5", 2.5), ("per_16p0", 16.0), ("per_84p0", 84.0), ("per_97p5", 97.5)):
         np.testing.assert_allclose(summ[key], np.percentile(lin, p, axis=0), rtol=1e-12)
+
+
+# ---- MTM proposals from the smooth indicator prior when there is no spatial prior -------------
+def _no_spatial(H, W, K):
+    from beetroots_b200 import modelling as M
+    prob = _synthetic(H, W, K)
+    p = prob.posterior
+    return prob, M.Posterior(p.D, p.L, p.N, p.likelihood, None, p.prior_indicator)      # separable: one site, all pixels
+
+
+def test_smooth_indicator_proposals_distribution(lib):
+    """Device draws (Philox) of sampler/utils/utils.py:50-97: with probability Z_u / (1 + Z_u) uniform in the box,
+    otherwise a generalised-Gaussian (power 4, scale delta) tail beyond the nearer bound, sides equally likely."""
+    from scipy import stats
+    from scipy.special import gamma
+    from beetroots_b200 import DevicePosterior
+    K = 384
+    prob, post = _no_spatial(8, 8, K)
+    pi = post.prior_indicator
+    lo, hi, delta = pi.lower_bounds, pi.upper_bounds, pi.indicator_margin_scale
+    dev = DevicePosterior.from_posterior(post)
+    try:
+        assert dev.n_sites == 1
+        dev.compute_all(prob.theta_init)
+        cand, us, ua = dev.debug_philox_mtm(0, K, 2024, 3)
+        cand2, _, _ = dev.debug_philox_mtm(0, K, 2024, 4)
+        assert not np.array_equal(cand, cand2)                                   # a fresh draw every iteration
+        x = cand.reshape(-1, post.D).astype(np.float64)
+        n = x.shape[0]
+        for d in range(post.D):
+            zu = 2 * (hi[d] - lo[d]) / (delta * gamma(0.25))
+            p_out = 1 / (1 + zu)
+            out = (x[:, d] < lo[d]) | (x[:, d] > hi[d])
+            assert abs(out.mean() - p_out) < 5 * np.sqrt(p_out * (1 - p_out) / n), (d, out.mean(), p_out)
+            inside = x[~out, d]
+            assert stats.kstest((inside - lo[d]) / (hi[d] - lo[d]), "uniform").pvalue > 1e-4
+            excess = np.where(x[out, d] > hi[d], x[out, d] - hi[d], x[out, d] - lo[d])
+            assert excess.size > 200
+            assert stats.kstest(excess, stats.gennorm(beta=4.0, scale=delta).cdf).pvalue > 1e-4
+            assert abs((excess > 0).mean() - 0.5) < 5 * 0.5 / np.sqrt(excess.size)
+        assert np.all((us > 0) & (us < 1)) and np.all((ua > 0) & (ua < 1))
+    finally:
+        dev.close()
+
+
+def test_mtm_without_spatial_prior_vs_oracle(lib):
+    """MTM on a separable posterior (likelihood + indicator, my_sampler.py:135-143 and posterior.py:105-110): the
+    Philox path equals the injected path bit for bit, and both follow the float64 oracle on the same candidates
+    (decisions identical up to near-ties, accepted states exact: they are copies of candidates)."""
+    from beetroots_b200 import DevicePosterior
+    from oracle.sampler import OracleSampler
+    K, seed = 12, 77
+    prob, post = _no_spatial(9, 7, K)
+    devs = [DevicePosterior.from_posterior(post) for _ in range(2)]
+    try:
+        nbr = -np.ones((post.N, 1), dtype=np.int32)
+        orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, K)
+        pi = post.prior_indicator
+        # start far from the mode (uniform in the box), otherwise no uniform proposal ever beats the current state
+        start = pi.lower_bounds + (pi.upper_bounds - pi.lower_bounds) * np.random.default_rng(5).uniform(size=(post.N, post.D))
+        start = start.astype(np.float32).astype(np.float64)
+        orc.init(start)
+        for dev in devs:
+            dev.compute_all(start)
+            dev.init_v_from_grad()
+        n_flip = 0
+        for t in range(1, 5):
+            obj_scale = np.abs(orc.current["objective_pix_chromatic"])
+            cand, us, ua = devs[0].debug_philox_mtm(0, K, seed, t)
+            for dev, inj in zip(devs, (False, True)):
+                dev.begin_iteration()
+                if inj:
+                    dev.mtm_site(0, K, seed, t, cand, us, ua)
+                else:
+                    dev.mtm_site(0, K, seed, t)
+                dev.mtm_finish(0.99)
+            th0, v0, _ = devs[0].get_state()
+            th1, v1, _ = devs[1].get_state()
+            assert np.array_equal(th0, th1) and np.array_equal(v0, v1)
+            o_acc, o_lrg = orc.mtm_step({0: {"cand": cand.astype(np.float64), "u_sel": us.astype(np.float64),
+                                             "u_acc": ua.astype(np.float64)}})
+            acc, lrg = devs[0].step_stats()
+            flips = np.where((acc > 0) != (o_acc > 0))[0]
+            for n in flips:
+                assert abs(lrg[n] - o_lrg[n]) < 1e-3 * (1 + abs(o_lrg[n])) + 1e-5 * obj_scale[n], (t, n, lrg[n], o_lrg[n])
+            n_flip += flips.size
+            same = (acc > 0) == (o_acc > 0)
+            # which candidate is selected is itself a float comparison: allow rare selection near-ties
+            bad = np.abs(th0 - orc.current["Theta"]).max(axis=1) > 1e-6
+            assert (bad & same).sum() <= 1, (t, np.where(bad & same)[0])
+            ok = same & ~bad
+            # the reference (and the oracle) form the denominator as (sum of all weights) - w_selected in float64
+            # (my_sampler.py:1142-1144): when the selected weight dominates, that difference carries an absolute error
+            # of one ulp of the total, i.e. 2.2e-16 e^{log_rg} relative to itself (0.15 at log_rg = 35, certain accept
+            # either way); the device sums the other weights directly
+            tol = 2e-3 * (1 + np.abs(o_lrg)) + 1e-5 * obj_scale + 2.3e-16 * np.exp(np.minimum(np.abs(o_lrg), 40.0))
+            viol = np.where(ok & ~(np.abs(lrg - o_lrg) <= tol))[0]
+            assert viol.size == 0, (t, viol, lrg[viol], o_lrg[viol], obj_scale[viol])
+            assert acc.sum() > 0
+            if flips.size or (bad & same).any():
+                from oracle import posterior as OP
+                orc.current = OP.compute_all(post, th0, nbr)
+                orc.v = v0.copy()
+        assert n_flip <= 2
+    finally:
+        for dev in devs:
+            dev.close()
