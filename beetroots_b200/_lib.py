@@ -68,6 +68,15 @@ SIGNATURES = {
     "bt_chain_get": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_double_p]),
     "bt_chain_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, c_double_p, c_double_p, c_double_p,
                                  c_double_p, c_double_p, c_double_p]),
+    "bt_model_check_snapshot_clppd": (C.c_int, [C.c_void_p]),
+    "bt_model_check_update_pvalues": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, c_float_p, c_float_p]),
+    "bt_optim_begin": (C.c_int, [C.c_void_p]),
+    "bt_optim_pmala_propose": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_int64, c_float_p]),
+    "bt_optim_update_v": (C.c_int, [C.c_void_p, C.c_double]),
+    "bt_optim_end": (C.c_int, [C.c_void_p, C.c_int]),
+    "bt_mtm_optim_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, c_float_p, c_uint8_p,
+                                       c_double_p]),
+    "bt_mtm_optim_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "bt_mlp_kernel_variant": (C.c_int, [C.c_void_p]),
     "bt_kernel_launches": (C.c_int64, [C.c_void_p]),
     "bt_mlp_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int64_p, c_int64_p]),

@@ -15,6 +15,7 @@
 #include "mlp_tc2.cuh"
 #include "mlp_tc3.cuh"
 #include "chain_kernels.cuh"
+#include "optim_kernels.cuh"
 
 static thread_local std::string g_err;
 static int fail(const char* what, const char* file, int line, cudaError_t e = cudaSuccess) {
@@ -59,6 +60,11 @@ struct bt_ctx {
     // online model checking accumulators (my_sampler.py:385-401)
     float *mc_clppd = nullptr, *mc_pvy = nullptr, *mc_pvl = nullptr;
     double mc_count = 0;
+    // optimisation mode (optim_kernels.cuh): snapshot of the state while a whole-map candidate is evaluated
+    float *snap_theta = nullptr, *snap_nll = nullptr, *snap_grad = nullptr, *snap_lf = nullptr;
+    bool snap_live = false;
+    double* colsum = nullptr;
+    int colsum_cap = 0;
     // on-device chain store (chain_kernels.cuh)
     float* chain = nullptr;
     int64_t chain_cap = 0, chain_len = 0;
@@ -146,7 +152,7 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
     tc3_free(c->tc3);
     void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
-                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl, c->chain};
+                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl, c->chain, c->snap_theta, c->snap_nll, c->snap_grad, c->snap_lf, c->colsum};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -748,7 +754,7 @@ extern "C" int bt_model_check_reset(bt_ctx* c) {
     return 0;
 }
 
-extern "C" int bt_model_check_update(bt_ctx* c, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject) {
+static int model_check_update_mode(bt_ctx* c, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject, int mode) {
     READY(c);
     REQUIRE((za_inject == nullptr) == (zm_inject == nullptr), "inject both noise arrays or none");
     if (!c->mc_clppd && bt_model_check_reset(c)) return -1;
@@ -758,11 +764,20 @@ extern "C" int bt_model_check_update(bt_ctx* c, uint64_t seed, int64_t t, const 
     const size_t nl = (size_t)c->N * c->L;
     if (stage_inject(c, za_inject, nl, &zad, tmp) || stage_inject(c, zm_inject, nl, &zmd, tmp)) { free_tmp(c, tmp); return -1; }
     model_check_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->N, c->L, c->lf_cache, c->obs, (float)c->mc_count, seed, t,
-                                                                   c->gid, zad, zmd, c->mc_clppd, c->mc_pvy, c->mc_pvl);
+                                                                   c->gid, zad, zmd, c->mc_clppd, c->mc_pvy, c->mc_pvl, mode);
     KLAUNCH(c);
-    c->mc_count += 1;
+    if (mode != 2) c->mc_count += 1;
     free_tmp(c, tmp);
     return 0;
+}
+extern "C" int bt_model_check_update(bt_ctx* c, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject) {
+    return model_check_update_mode(c, seed, t, za_inject, zm_inject, 0);
+}
+// optimisation mode (my_sampler.py:208-212, 222-256): clppd is the snapshot exp(-nll) of the best iterate so far, the
+// p-values are estimated at the end from ESS_OPTIM replications at the final iterate
+extern "C" int bt_model_check_snapshot_clppd(bt_ctx* c) { return model_check_update_mode(c, 0, 0, nullptr, nullptr, 2); }
+extern "C" int bt_model_check_update_pvalues(bt_ctx* c, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject) {
+    return model_check_update_mode(c, seed, t, za_inject, zm_inject, 1);
 }
 
 extern "C" int bt_model_check_get(bt_ctx* c, double* clppd, double* pval_y, double* pval_llh, int finalize) {
@@ -876,4 +891,118 @@ extern "C" int bt_chain_stats(bt_ctx* c, int64_t first, int64_t count, int n_q, 
     cudaStreamSynchronize(c->stream);
     cudaFree(outbuf);
     return rc;
+}
+
+// ---- optimisation mode -----------------------------------------------------------------------------------
+static int ensure_snapshot(bt_ctx* c) {
+    if (c->snap_theta) return 0;
+    const size_t N = c->N, D = c->D, L = c->L;
+    CK(cudaMalloc(&c->snap_theta, N * D * 4)); CK(cudaMalloc(&c->snap_nll, N * 4));
+    CK(cudaMalloc(&c->snap_grad, N * D * 4)); CK(cudaMalloc(&c->snap_lf, N * L * 4));
+    return 0;
+}
+
+extern "C" int bt_optim_begin(bt_ctx* c) {
+    READY(c);
+    CK(cudaSetDevice(c->device));
+    if (ensure_snapshot(c)) return -1;
+    const size_t N = c->N, D = c->D, L = c->L;
+    CK(cudaMemcpyAsync(c->snap_theta, c->theta, N * D * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->snap_nll, c->nll_lik, N * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->snap_grad, c->grad_lik, N * D * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->snap_lf, c->lf_cache, N * L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->snap_live = true;
+    return 0;
+}
+
+extern "C" int bt_optim_pmala_propose(bt_ctx* c, double eps, double eta, int with_noise, uint64_t seed, int64_t t,
+                                      const float* z_inject) {
+    READY(c);
+    REQUIRE(c->snap_live, "bt_optim_begin was not called");
+    CK(cudaSetDevice(c->device));
+    std::vector<void*> tmp;
+    float* zd;
+    if (stage_inject(c, with_noise ? z_inject : nullptr, (size_t)c->N * c->D, &zd, tmp)) { free_tmp(c, tmp); return -1; }
+    optim_pmala_propose_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->N, c->D, c->max_degree, c->snap_theta,
+        c->nbr, c->snap_grad, c->v, (float)eps, (float)eta, with_noise, seed, t, c->gid, zd, c->theta);
+    KLAUNCH(c);
+    free_tmp(c, tmp);
+    return 0;
+}
+
+extern "C" int bt_optim_update_v(bt_ctx* c, double alpha) {
+    READY(c);
+    CK(cudaSetDevice(c->device));
+    optim_update_v_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->N, c->D, c->max_degree, c->theta, c->nbr,
+                                                                      c->grad_lik, (float)alpha, c->v);
+    KLAUNCH(c);
+    return 0;
+}
+
+extern "C" int bt_optim_end(bt_ctx* c, int accept) {
+    READY(c);
+    REQUIRE(c->snap_live, "bt_optim_begin was not called");
+    CK(cudaSetDevice(c->device));
+    if (!accept) {
+        const size_t N = c->N, D = c->D, L = c->L;
+        CK(cudaMemcpyAsync(c->theta, c->snap_theta, N * D * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->nll_lik, c->snap_nll, N * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->grad_lik, c->snap_grad, N * D * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->lf_cache, c->snap_lf, N * L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->snap_live = false;
+    return 0;
+}
+
+extern "C" int bt_mtm_optim_weights(bt_ctx* c, int site, int K, uint64_t seed, int64_t t, const float* cand_inject,
+                                    const uint8_t* owned, double* colsum_out) {
+    READY(c);
+    REQUIRE(site >= 0 && site < c->n_sites, "no such site");
+    REQUIRE(K >= 1 && colsum_out, "bad arguments");
+    REQUIRE(c->pr.has_indicator, "The Posterior has no specified smooth indicator prior");   // my_sampler.py:132-133
+    CK(cudaSetDevice(c->device));
+    const int n_pix = c->site_size[site];
+    for (int k = 0; k < K; ++k) colsum_out[k] = 0.0;
+    if (n_pix == 0) return 0;
+    const int* sp = c->site_pix + c->site_off[site];
+    const size_t M = (size_t)n_pix * (K + 1);
+    REQUIRE(M < (size_t)1 << 31, "too many candidate rows for one launch");
+    if (ensure_rows(c, M, false)) return -1;
+    if (K > c->colsum_cap) {
+        if (c->colsum) cudaFree(c->colsum);
+        CK(cudaMalloc(&c->colsum, (size_t)K * sizeof(double)));
+        c->colsum_cap = K;
+    }
+    const uint8_t* od;
+    if (upload_owned(c, owned, &od)) return -1;
+    std::vector<void*> tmp;
+    float* cd;
+    if (stage_inject(c, cand_inject, (size_t)c->N * K * c->D, &cd, tmp)) { free_tmp(c, tmp); return -1; }
+    mtm_gen_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->pr, n_pix, sp, c->D, K, c->max_degree, c->theta,
+        c->nbr, seed, t, site, c->gid, cd, c->rows);
+    KLAUNCH(c);
+    if (run_mlp(c, c->rows, (int)M, c->lf_rows, nullptr)) { free_tmp(c, tmp); return -1; }
+    mtm_optim_nl_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(c->pr, c->fm, n_pix, sp, c->D, c->L, K,
+        c->max_degree, c->theta, c->nbr, c->obs, c->rows, c->lf_rows, c->nl);
+    KLAUNCH(c);
+    mtm_optim_colsum_kernel<<<K, 256, 0, c->stream>>>(n_pix, sp, K, c->nl, od, c->colsum);
+    KLAUNCH(c);
+    CK(cudaMemcpyAsync(colsum_out, c->colsum, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    free_tmp(c, tmp);
+    return 0;
+}
+
+extern "C" int bt_mtm_optim_select(bt_ctx* c, int site, int K, int k_star) {
+    READY(c);
+    REQUIRE(site >= 0 && site < c->n_sites, "no such site");
+    REQUIRE(K >= 1 && k_star >= 0 && k_star < K, "challenger index out of range");
+    CK(cudaSetDevice(c->device));
+    const int n_pix = c->site_size[site];
+    if (n_pix == 0) return 0;
+    REQUIRE((size_t)n_pix * (K + 1) <= c->rows_cap, "bt_mtm_optim_weights was not called for this site");
+    mtm_optim_select_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(n_pix, c->site_pix + c->site_off[site], c->D, K,
+        k_star, c->rows, c->nl, c->theta, c->accept, c->accepted_any);
+    KLAUNCH(c);
+    return 0;
 }

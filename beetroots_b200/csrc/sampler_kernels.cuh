@@ -576,7 +576,8 @@ __global__ void mtm_finish_kernel(PriorDev pr, FmapDev fm, int N, int D, int L, 
 __global__ void model_check_kernel(int N, int L, const float* __restrict__ lf_cache, const ObsConst* __restrict__ obs,
                                    float count, uint64_t seed, int64_t t, const int64_t* __restrict__ gid,
                                    const float* __restrict__ za_inject, const float* __restrict__ zm_inject,
-                                   float* __restrict__ clppd, float* __restrict__ pvy, float* __restrict__ pvl) {
+                                   float* __restrict__ clppd, float* __restrict__ pvy, float* __restrict__ pvl, int mode) {
+    // mode 0: sampling branch (everything); 1: p-values only; 2: clppd <- exp(-nll) (optimisation branch, :208-212)
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const int64_t g = gid ? gid[n] : (int64_t)n;
@@ -589,6 +590,7 @@ __global__ void model_check_kernel(int N, int L, const float* __restrict__ lf_ca
         const float lf = lf_cache[(size_t)n * L + l];
         float nll, dummy;
         mixing_line<false>(lf, u.o, nll, dummy);
+        if (mode == 2) { clppd[(size_t)n * L + l] = expf(-nll); continue; }
         float za, zm;
         if (za_inject) {
             za = za_inject[(size_t)n * L + l];
@@ -613,10 +615,10 @@ __global__ void model_check_kernel(int N, int L, const float* __restrict__ lf_ca
         nll_sum += nll;
         nll_rep_sum += nll_rep;
         const size_t idx = (size_t)n * L + l;
-        clppd[idx] = clppd[idx] * wgt_old + expf(-nll) * wgt_new;
+        if (mode == 0) clppd[idx] = clppd[idx] * wgt_old + expf(-nll) * wgt_new;
         pvy[idx] = pvy[idx] * wgt_old + ((yr_rep <= u.o.yr) ? wgt_new : 0.f);
     }
-    pvl[n] = pvl[n] * wgt_old + ((nll_rep_sum >= nll_sum) ? wgt_new : 0.f);
+    if (mode != 2) pvl[n] = pvl[n] * wgt_old + ((nll_rep_sum >= nll_sum) ? wgt_new : 0.f);
 }
 
 // ---- reductions -----------------------------------------------------------------------------

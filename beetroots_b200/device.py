@@ -343,6 +343,50 @@ class DevicePosterior:
                 "bt_model_check_get")
         return clppd, pvy, pvl
 
+    def model_check_snapshot_clppd(self):
+        """optimisation branch of _update_model_check_values (sampler/my_sampler.py:208-212)."""
+        L.check(self._lib.bt_model_check_snapshot_clppd(self._ctx), "bt_model_check_snapshot_clppd")
+
+    def model_check_update_pvalues(self, seed, t, za=None, zm=None):
+        """one replication of _finalize_model_check_values, optimisation branch (sampler/my_sampler.py:222-256)."""
+        za, zm = L.as_f32(za), L.as_f32(zm)
+        L.check(self._lib.bt_model_check_update_pvalues(self._ctx, seed, t, L.dptr(za, C.c_float), L.dptr(zm, C.c_float)),
+                "bt_model_check_update_pvalues")
+
+    # ------------------------------------------------------------------ optimisation mode (is_stochastic=False)
+    def optim_pmala_step(self, eps, eta, alpha, seed, t, z=None):
+        """generate_new_sample_pmala_rmsprop, optimisation branch (sampler/my_sampler.py:908-964) -> (accept, proba)."""
+        obj_cur = self.objective_terms()["objective"]
+        L.check(self._lib.bt_optim_begin(self._ctx), "bt_optim_begin")
+        z = L.as_f32(z)
+        accept = False
+        for with_noise in (0, 1):
+            L.check(self._lib.bt_optim_pmala_propose(self._ctx, eps, eta, with_noise, seed, t, L.dptr(z, C.c_float)),
+                    "bt_optim_pmala_propose")
+            self.refresh()
+            if self.objective_terms()["objective"] < obj_cur:
+                accept = True
+                break
+        L.check(self._lib.bt_optim_update_v(self._ctx, alpha), "bt_optim_update_v")
+        L.check(self._lib.bt_optim_end(self._ctx, int(accept)), "bt_optim_end")
+        return accept, (1 if accept else 0)
+
+    def mtm_optim_weights(self, site, K, seed, t, cand=None, owned=None) -> np.ndarray:
+        cand = L.as_f32(cand)
+        ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+        out = np.zeros(K)
+        L.check(self._lib.bt_mtm_optim_weights(self._ctx, site, K, seed, t, L.dptr(cand, C.c_float), L.dptr(ow, C.c_uint8),
+                                               L.dptr(out)), "bt_mtm_optim_weights")
+        return out
+
+    def mtm_optim_select(self, site, K, k_star):
+        L.check(self._lib.bt_mtm_optim_select(self._ctx, site, K, int(k_star)), "bt_mtm_optim_select")
+
+    def mtm_optim_site(self, site, K, seed, t, cand=None):
+        """body of the site loop of generate_new_sample_mtm, optimisation branch (sampler/my_sampler.py:1006-1086)."""
+        colsum = self.mtm_optim_weights(site, K, seed, t, cand)
+        self.mtm_optim_select(site, K, int(np.argmin(colsum)))
+
     def synchronize(self):
         L.check(self._lib.bt_synchronize(self._ctx), "bt_synchronize")
 

@@ -205,6 +205,38 @@ class ShardedDevicePosterior:
         return {"nll": np.float64(vec[0]), "nl_prior_spatial": vec[1:1 + D], "nl_prior_indicator": vec[1 + D:1 + 2 * D],
                 "objective": float(vec[-1])}
 
+    # ---- optimisation mode: same steps as DevicePosterior, with the halo exchange and the global reductions in between
+    def optim_pmala_step(self, eps, eta, alpha, seed, t, z=None):
+        loc, lib = self.local, self.local._lib
+        from . import _lib as L
+        import ctypes as C
+        obj_cur = self.objective_terms()["objective"]
+        L.check(lib.bt_optim_begin(loc._ctx), "bt_optim_begin")
+        z = L.as_f32(z if z is None or self.world == 1 else np.asarray(z)[self.plan.local_global_id])
+        accept = False
+        for with_noise in (0, 1):
+            L.check(lib.bt_optim_pmala_propose(loc._ctx, eps, eta, with_noise, seed, t, L.dptr(z, C.c_float)),
+                    "bt_optim_pmala_propose")
+            self.halo_exchange()        # ghost rows see an incomplete stencil: take the owner's values
+            loc.refresh()
+            if self.objective_terms()["objective"] < obj_cur:
+                accept = True
+                break
+        L.check(lib.bt_optim_update_v(loc._ctx, alpha), "bt_optim_update_v")
+        L.check(lib.bt_optim_end(loc._ctx, int(accept)), "bt_optim_end")
+        return accept, (1 if accept else 0)
+
+    def mtm_optim_site(self, site, K, seed, t, cand=None):
+        colsum = self._allreduce(self.local.mtm_optim_weights(site, K, seed, t, cand, self._owned))
+        self.local.mtm_optim_select(site, K, int(np.argmin(colsum)))
+        self.halo_exchange()
+
+    def model_check_snapshot_clppd(self):
+        self.local.model_check_snapshot_clppd()
+
+    def model_check_update_pvalues(self, seed, t, za=None, zm=None):
+        self.local.model_check_update_pvalues(seed, t, za, zm)
+
     def spatial_prior_unweighted(self):
         return self._allreduce(self.local.spatial_prior_unweighted(self._owned))
 

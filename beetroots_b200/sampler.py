@@ -52,6 +52,8 @@ class MySamplerParams:
 
 
 class B200Sampler:
+    ESS_OPTIM = 1_000                                                              # sampler/abstract_sampler.py:15
+
     def __init__(self, my_sampler_params, D: int, L: int, N: int,
                  rng: np.random.Generator = None, device: int = 0, mlp_mode: int = MLP_FP32,
                  device_chain: int = 0, device_chain_thin: int = 1):
@@ -64,9 +66,6 @@ class B200Sampler:
         assert np.sum(self.selection_probas) == 1, f"{self.selection_probas} should sum to 1"
         self.stochastic = p.is_stochastic
         self.compute_correction_term = p.compute_correction_term
-        if not self.stochastic:
-            raise NotImplementedError("optimisation mode (is_stochastic=False) is not on the GPU path yet "
-                                      "(SURVEY.md §8f rank 4)")
         if self.compute_correction_term:
             raise NotImplementedError("the PMALA correction term needs the Hessian diagonal, which the reference "
                                       "itself cannot evaluate with a spatial prior (posterior.py:259); "
@@ -145,6 +144,9 @@ class B200Sampler:
     def generate_new_sample_pmala_rmsprop(self, t: int, posterior, noise: Optional[dict] = None):
         """sampler/my_sampler.py:718-906.  ``noise[s] = {"z": (N, D), "u": (N,)}`` injects the draws."""
         dev = self.attach(posterior)
+        if not self.stochastic:                                                    # :908-964, noise = {"z": (N, D)}
+            return dev.optim_pmala_step(self.eps0, self.lambda_, self.alpha, self.philox_seed or 0, t,
+                                        None if noise is None else noise.get("z"))
         dev.begin_iteration()
         for s in range(dev.n_sites):
             nz = noise[dev.site_keys[s]] if noise is not None else {}
@@ -158,9 +160,14 @@ class B200Sampler:
         dev.begin_iteration()
         for s in range(dev.n_sites):
             nz = noise[dev.site_keys[s]] if noise is not None else {}
-            dev.mtm_site(s, self.k_mtm, self.philox_seed or 0, t, nz.get("cand"), nz.get("u_sel"), nz.get("u_acc"))
+            if self.stochastic:
+                dev.mtm_site(s, self.k_mtm, self.philox_seed or 0, t, nz.get("cand"), nz.get("u_sel"), nz.get("u_acc"))
+            else:                                                                  # :1050-1086
+                dev.mtm_optim_site(s, self.k_mtm, self.philox_seed or 0, t, nz.get("cand"))
         dev.mtm_finish(self.alpha)
         acc, lpa = dev.reduce_step_stats()
+        if not self.stochastic:
+            return acc / self.N, acc / self.N                                      # :1199-1200
         return acc / self.N, lpa / self.N
 
     def sample_regu_hyperparams(self, posterior, regu_weights_optimizer, t: int, current_Theta=None) -> np.ndarray:
@@ -215,6 +222,7 @@ class B200Sampler:
         assert np.sum(np.isinf(self.v)) == 0.0
         self.j_t = np.zeros((self.N * self.D,))
         dev.model_check_reset()                                                    # :385-401
+        best_objective = np.inf                                                    # used only if not self.stochastic
         regu_weights_optimizer = EBayesMMLELogRate(scale=regu_spatial_scale, N0=regu_spatial_N0, N1=+np.inf,
                                                    dim=self.D * self.N, vmin=regu_spatial_vmin, vmax=regu_spatial_vmax,
                                                    homogeneity=2.0, exponent=0.8)           # :369-379
@@ -252,7 +260,11 @@ class B200Sampler:
                 additional_sampling_log["log_proba_accept_t"] = log_proba_accept_t
                 dict_objective = dev.objective_terms()                             # posterior.py:270-330
                 if t > T_BI:                                                       # :468-476 / :514-521
-                    dev.model_check_update(self.philox_seed, t)
+                    if self.stochastic:
+                        dev.model_check_update(self.philox_seed, t)
+                    elif dict_objective["objective"] < best_objective:            # :208-212
+                        best_objective = dict_objective["objective"] * 1
+                        dev.model_check_snapshot_clppd()
                 kw = dict(Theta=self.current["Theta"], forward_map_evals=self.current["forward_map_evals"],
                           nll_utils=self.current["nll_utils"], dict_objective=dict_objective,
                           additional_sampling_log=additional_sampling_log)
@@ -266,6 +278,9 @@ class B200Sampler:
                     and dev.chain_length() < self.device_chain):
                 dev.chain_push()
         self._pull_state(with_current=True)
+        if not self.stochastic:                                                    # :222-256: p-values at the estimate
+            for rep in range(self.ESS_OPTIM):
+                dev.model_check_update_pvalues(self.philox_seed, max_iter + 1 + rep)
         clppd, p_values_y, p_values_llh = dev.model_check_get(finalize=True)       # :544-549
         saver.save_additional(list_arrays=[clppd, p_values_y, p_values_llh],
                               list_names=["clppd", "p-values-y", "p-values-llh"])   # :551-558

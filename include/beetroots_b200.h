@@ -161,6 +161,35 @@ int bt_model_check_reset(bt_ctx* ctx);
 int bt_model_check_update(bt_ctx* ctx, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject);
 int bt_model_check_get(bt_ctx* ctx, double* clppd, double* pval_y, double* pval_llh, int finalize);
 
+/* optimisation mode of the model check (sampler/my_sampler.py:208-212, 222-256): clppd <- exp(-nll) of the resident
+ * iterate (call when the objective improved); p-values only (ESS_OPTIM replications at the final iterate). */
+int bt_model_check_snapshot_clppd(bt_ctx* ctx);
+int bt_model_check_update_pvalues(bt_ctx* ctx, uint64_t seed, int64_t t, const float* za_inject, const float* zm_inject);
+
+/* ---- optimisation mode (MySamplerParams.is_stochastic = False) -----------------------------------------------
+ * PMALA branch, sampler/my_sampler.py:908-964 -- a whole-map candidate is evaluated in place and kept only if the
+ * global objective decreases:
+ *   bt_optim_begin            snapshot Theta and the cached likelihood terms
+ *   bt_optim_pmala_propose    Theta <- Theta_snap - eps/2 G grad(Theta_snap) [+ sqrt(eps G) z if with_noise]  (:913-940);
+ *                             z_inject (N, D) HOST float or NULL (Philox).  Then: (halo exchange,) bt_compute_all,
+ *                             bt_objective_terms -> compare on the host (all-reduce when sharded)
+ *   bt_optim_update_v         v <- alpha v + (1 - alpha) grad(Theta)^2 at the last evaluated candidate (:952-953)
+ *   bt_optim_end              accept != 0 keeps the candidate, 0 restores the snapshot
+ * MTM branch, sampler/my_sampler.py:1006-1086, one colour class:
+ *   bt_mtm_optim_weights      candidates + their negative log conditional posterior (no proposal density);
+ *                             colsum_out[k] (K, HOST) = sum over the class's pixels (flagged in owned, or all) of nl[i, k]
+ *                             -> the caller takes the argmin (after an all-reduce when sharded) (:1051-1053)
+ *   bt_mtm_optim_select       keep candidate k_star where it improves on the current value (:1073-1086)
+ * followed by bt_mtm_finish after all classes, as in sampling mode (:1182-1197). */
+int bt_optim_begin(bt_ctx* ctx);
+int bt_optim_pmala_propose(bt_ctx* ctx, double eps, double eta, int with_noise, uint64_t seed, int64_t t,
+                           const float* z_inject);
+int bt_optim_update_v(bt_ctx* ctx, double alpha);
+int bt_optim_end(bt_ctx* ctx, int accept);
+int bt_mtm_optim_weights(bt_ctx* ctx, int site, int K, uint64_t seed, int64_t t, const float* cand_inject,
+                         const uint8_t* owned, double* colsum_out);
+int bt_mtm_optim_select(bt_ctx* ctx, int site, int K, int k_star);
+
 /* ---- on-device chain store and posterior summaries ------------------------------------------------------
  * Replaces the round trip saver memory -> HDF5 `list_Theta` (sampler/saver/my_saver.py:46-83, abstract_saver.py:190-213)
  * -> per-pixel re-read + np.mean / np.percentile (inversion/results/utils/mc.py:158-215): the (thinned) chain stays in

@@ -201,3 +201,58 @@ class OracleSampler:
             self.v = np.where(accept_total[:, None] > 0,
                               self.alpha * self.v + (1 - self.alpha) * self.current["grad"] ** 2, self.v)
         return accept_total, log_rg_total
+
+    # ------------------------------------------------------------------ optimisation mode (is_stochastic=False)
+    def pmala_optim_step(self, z):
+        """generate_new_sample_pmala_rmsprop, optimisation branch (my_sampler.py:908-964).  z (N, D) standard normals."""
+        post = self.post
+        key = "objective_global"
+        grad_t = self.current["grad"]
+        G = 1 / (self.lambda_ + np.sqrt(self.v))                                   # :915
+        z_t = z * np.sqrt(self.eps0 * G)                                           # :922-923
+        mu = self.current["Theta"] - self.eps0 / 2 * G * grad_t                    # :926-928
+        cand_all = P.compute_all(post, mu, self.nbr)
+        if cand_all[key] < self.current[key]:                                      # :935-938
+            self.current = cand_all
+            accept = True
+        else:
+            cand_all = P.compute_all(post, mu + z_t, self.nbr)                     # :940-945
+            accept = bool(cand_all[key] < self.current[key])
+            if accept:
+                self.current = cand_all
+        self.v = self.alpha * self.v + (1 - self.alpha) * cand_all["grad"] ** 2    # :952-953 (last evaluated candidate)
+        return accept, (1 if accept else 0)
+
+    def mtm_optim_step(self, noise: dict):
+        """generate_new_sample_mtm, optimisation branch (my_sampler.py:1006-1086, 1182-1200).  noise[s] = {"cand"}."""
+        post = self.post
+        K = self.k_mtm
+        new_Theta = self.current["Theta"] * 1
+        accept_total = np.zeros(self.N)
+        list_idx = self.sites()
+        chromatic = len(list_idx) > 1
+        for s in list_idx:
+            idx_pix = post.dict_sites[s]
+            n_pix = idx_pix.size
+            cand_pix = np.zeros((n_pix, K + 1, self.D))
+            cand_pix[:, :K] = noise[s]["cand"]
+            cand_pix[:, K] = new_Theta[idx_pix]
+            nl = np.zeros((n_pix, K + 1))
+            if post.prior_spatial is not None:
+                had, _ = P.spatial_sums(new_Theta, self.nbr, idx_pix, cand_pix)
+                factor = 1.0 if (chromatic or n_pix < self.N) else 0.5
+                nl += factor * (post.prior_spatial.weights * had).sum(-1)
+            if post.prior_indicator is not None:
+                nl += P.indicator_penalty(cand_pix, post.prior_indicator)
+            fm = P.forward_map_compute_all(post.likelihood.forward_map, cand_pix.reshape(n_pix * (K + 1), self.D), False)
+            nl += P.likelihood_eval(post.likelihood, fm, idx_pix, False)["nll_pix"].reshape(n_pix, K + 1)
+            k_star = int(np.argmin(nl[:, :-1].sum(axis=0)))                        # :1051-1053 (one index per class)
+            nc, n0 = nl[:, k_star], nl[:, -1]
+            acc = (nc < n0) & np.isfinite(nc) & np.isfinite(n0)                    # :1073-1077
+            new_Theta[idx_pix] = np.where(acc[:, None], cand_pix[:, k_star], cand_pix[:, K])
+            accept_total[idx_pix] = acc
+        if accept_total.max() > 0:                                                 # :1182-1197
+            self.current = P.compute_all(post, new_Theta, self.nbr)
+            self.v = np.where(accept_total[:, None] > 0,
+                              self.alpha * self.v + (1 - self.alpha) * self.current["grad"] ** 2, self.v)
+        return accept_total

@@ -286,3 +286,105 @@ def test_mtm_without_spatial_prior_vs_oracle(lib):
     finally:
         for dev in devs:
             dev.close()
+
+
+# ---- optimisation mode (is_stochastic=False) -------------------------------------
+@pytest.mark.parametrize("name", ["ref_n4_6x5", "ref_n8_5x6_censored"])
+def test_optimisation_mode_vs_reference_golden(lib, name):
+    """Device PMALA / MTM optimisation steps with the reference's recorded noise (tests/golden/*_optim.npz):
+    accept decisions identical, states within rtol 1e-5, v within 2e-5 of its scale, objective within 1e-6."""
+    from beetroots_b200 import B200Sampler, MySamplerParams
+    g, go = load_golden(name), load_golden(name + "_optim")
+    post, _ = problem_from_golden(g)
+    K = int(g["K"])
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, False, False), post.D, post.L, post.N)
+    dev = smp.attach(post)
+    dev.compute_all(g["theta0"])
+    dev.init_v_from_grad()
+    for t, kind in enumerate(go["kernels"], start=1):
+        if kind == 1:
+            acc, proba = smp.generate_new_sample_pmala_rmsprop(t, post, noise={"z": go[f"t{t}_z"]})
+            assert float(acc) == float(go[f"t{t}_accept"]) and proba == int(acc)
+        else:
+            full = {}
+            for s, idx in post.dict_sites.items():
+                c = np.zeros((post.N, K, post.D))
+                c[idx] = go[f"t{t}_s{s}_cand"]
+                full[s] = {"cand": c}
+            acc_mean, acc_mean2 = smp.generate_new_sample_mtm(t, post, noise=full)
+            a, _ = dev.step_stats()
+            assert np.array_equal(a, go[f"t{t}_accept"]) and acc_mean == acc_mean2 == a.mean()
+        th, v, _ = dev.get_state()
+        np.testing.assert_allclose(th, go[f"t{t}_Theta"], rtol=1e-5, atol=2e-6)
+        assert np.max(np.abs(v - go[f"t{t}_v"])) <= 2e-5 * np.abs(go[f"t{t}_v"]).max()
+        obj = dev.objective_terms()["objective"]
+        assert abs(obj - float(go[f"t{t}_objective"])) < 1e-6 * abs(float(go[f"t{t}_objective"]))
+    dev.close()
+
+
+def test_optimisation_pmala_retry_and_reject_vs_oracle(lib):
+    """Step sizes large enough that the plain gradient step overshoots: the noisy retry (my_sampler.py:939-950) and the
+    rejection (state restored, v still updated with the rejected candidate's gradient, :952-953) against the oracle."""
+    from beetroots_b200 import DevicePosterior
+    from beetroots_b200.modelling import build_neighbor_table
+    from oracle.sampler import OracleSampler
+    prob = _synthetic(9, 8, 4)
+    post = prob.posterior
+    nbr = build_neighbor_table(post.prior_spatial.list_edges, post.N, 4)
+    seen = set()
+    for eps in (1e-4, 3e-2, 1.0):
+        dev = DevicePosterior.from_posterior(post)
+        orc = OracleSampler(post, nbr, eps, 1e-5, 0.99, 4)
+        orc.init(prob.theta_init)
+        dev.compute_all(prob.theta_init)
+        dev.init_v_from_grad()
+        rng = np.random.default_rng(int(eps * 1e6))
+        for t in range(1, 5):
+            z = rng.standard_normal((post.N, post.D)).astype(np.float32)
+            before = orc.current["Theta"].copy()
+            step_std = np.sqrt(eps / (1e-5 + np.sqrt(orc.v)))
+            o_acc, _ = orc.pmala_optim_step(z.astype(np.float64))
+            acc, _ = dev.optim_pmala_step(eps, 1e-5, 0.99, 0, t, z)
+            assert bool(acc) == bool(o_acc), (eps, t)
+            th, v, _ = dev.get_state()
+            if not acc:
+                assert np.array_equal(th.astype(np.float32), before.astype(np.float32))      # restored exactly
+            # same float32 bound as the sampling-mode chain test: rounding of nearly cancelling gradients is amplified by
+            # the preconditioner, at most 0.5 % of the local step scale sqrt(eps G)
+            assert np.all(np.abs(th - orc.current["Theta"]) <= 1e-5 * np.abs(th) + 2e-6 + 5e-3 * step_std)
+            assert np.max(np.abs(v - orc.v)) <= 1e-4 * np.abs(orc.v).max()
+            cur = dev.get_current()
+            np.testing.assert_allclose(cur["objective_global"], orc.current["objective_global"], rtol=1e-6)
+            seen.add(bool(acc))
+        dev.close()
+    assert seen == {True, False}, "both the accepted and the rejected branch must be exercised"
+
+
+def test_sample_in_optimisation_mode(lib):
+    """Full ``sample`` loop with is_stochastic=False: the objective never increases, clppd is exp(-nll) of the best
+    saved iterate (my_sampler.py:208-212), p-values come from ESS_OPTIM replications at the final iterate (:222-256)."""
+    from beetroots_b200 import B200Sampler, MySamplerParams
+    prob = _synthetic(8, 8, 6)
+    post = prob.posterior
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.3, 0.7], 6, False, False), post.D, post.L, post.N,
+                      rng=np.random.default_rng(5))
+    smp.ESS_OPTIM = 40
+    objs = []
+
+    class Saver(_MemSaver):
+        def update_memory(self, t, Theta, dict_objective, **kw):
+            objs.append(dict_objective["objective"])
+            self.Theta.append(Theta.copy())
+
+    sv = Saver()
+    smp.sample(post, sv, 12, Theta_0=prob.theta_init, disable_progress_bar=True)
+    assert len(objs) == 12 and np.all(np.diff(objs) <= 1e-6 * np.abs(objs[0])), objs
+    assert objs[-1] < objs[0]
+    clppd, pvy, pvl = sv.additional["clppd"], sv.additional["p-values-y"], sv.additional["p-values-llh"]
+    from oracle import posterior as OP
+    from beetroots_b200.modelling import build_neighbor_table
+    fm = OP.forward_map_compute_all(post.likelihood.forward_map, sv.Theta[int(np.argmin(objs))], False)
+    nll_full = OP.likelihood_eval(post.likelihood, fm, None, False)["nll_full"]
+    np.testing.assert_allclose(clppd, np.exp(-nll_full), rtol=2e-4, atol=1e-30)
+    assert np.all((pvy >= 0) & (pvy <= 0.5)) and np.all((pvl >= 0) & (pvl <= 1))
+    assert np.allclose(pvy * 40, np.round(pvy * 40), atol=1e-3) and pvl.std() > 0

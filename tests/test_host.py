@@ -88,8 +88,10 @@ def test_sampler_params_asserts_and_deepcopy():
     a = s.rng.standard_normal(3)
     s.set_rng_state(bytes(st), bytes(inc))
     assert np.array_equal(a, s.rng.standard_normal(3))
-    with pytest.raises(NotImplementedError):
-        B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], 10, False, False), 4, 10, 12)
+    with pytest.raises(NotImplementedError):          # the Hessian-diagonal correction term (posterior.py:259) is not built
+        B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], 10, True, True), 4, 10, 12)
+    opt = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], 10, False, False), 4, 10, 12)
+    assert opt.stochastic is False and copy.deepcopy(opt).stochastic is False
 
 
 def test_likelihood_mirror_shape_error():

@@ -153,3 +153,25 @@ def test_regu_weight_optimiser_and_potential_vs_reference_golden(key):
             tau = opt.update(tau, t, float(gX.sum()))
         np.testing.assert_allclose(tau, ref["tau"][t - 1], rtol=1e-12)
         np.testing.assert_allclose(opt.mean_theta, ref["mean_theta"][t - 1], rtol=1e-12)
+
+
+# ---- optimisation mode (is_stochastic=False): oracle vs the tapes recorded from the reference ----
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_optimisation_mode_matches_reference(name):
+    """tests/golden/make_golden_optim.py ran MySampler(is_stochastic=False); replaying its noise through
+    OracleSampler.pmala_optim_step / mtm_optim_step reproduces every state (my_sampler.py:908-964, 1050-1086)."""
+    g = load_golden(name)
+    go = load_golden(name + "_optim")
+    post, nbr = problem_from_golden(g)
+    orc = OracleSampler(post, nbr, 1e-4, 1e-5, 0.99, int(g["K"]))
+    orc.init(g["theta0"])
+    for t, kind in enumerate(go["kernels"], start=1):
+        if kind == 1:
+            acc, _ = orc.pmala_optim_step(go[f"t{t}_z"])
+            assert float(acc) == float(go[f"t{t}_accept"])
+        else:
+            acc = orc.mtm_optim_step({s: {"cand": go[f"t{t}_s{s}_cand"]} for s in post.dict_sites})
+            assert np.array_equal(acc, go[f"t{t}_accept"])
+        assert rel(orc.current["Theta"], go[f"t{t}_Theta"]) < 1e-9
+        assert rel(orc.v, go[f"t{t}_v"]) < 1e-8
+        assert abs(orc.current["objective_global"] - float(go[f"t{t}_objective"])) < 1e-8 * abs(float(go[f"t{t}_objective"]))
