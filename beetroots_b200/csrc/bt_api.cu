@@ -646,11 +646,23 @@ extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t,
         c->nbr, seed, t, site, c->gid, cd, c->rows);
     KLAUNCH(c);
     if (run_mlp(c, c->rows, (int)M, c->lf_rows, nullptr)) { free_tmp(c, tmp); return -1; }
-    const size_t mtm_smem = (size_t)MTM_WARPS * ((1u << c->max_degree) - 1u) * (BT_MAX_D + 1) * sizeof(float);
-    mtm_select_kernel<<<(n_pix + MTM_WARPS - 1) / MTM_WARPS, MTM_WARPS * 32, mtm_smem, c->stream>>>(c->pr, c->fm,
-        n_pix, sp, c->D, c->L, K, c->max_degree, c->n_sites > 1, c->theta, c->nbr, c->obs, c->jt, c->rows, c->lf_rows, c->nl,
-        seed, t, site, c->gid, usd, uad, c->accept, c->logpa, c->accepted_any);
-    KLAUNCH(c);
+    static const bool split_off = getenv("BT_MTM_NOSPLIT") != nullptr;
+    if (c->max_degree <= 4 && !split_off) {
+        // degree <= 4: weights by one thread per candidate row, then selection by one warp per pixel
+        mtm_nl_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(c->pr, c->fm, n_pix, sp, c->D, c->L, K, c->max_degree,
+            c->theta, c->nbr, c->obs, c->rows, c->lf_rows, c->nl);
+        KLAUNCH(c);
+        mtm_select_kernel<true><<<(n_pix + MTM_WARPS - 1) / MTM_WARPS, MTM_WARPS * 32, 0, c->stream>>>(c->pr, c->fm,
+            n_pix, sp, c->D, c->L, K, c->max_degree, c->n_sites > 1, c->theta, c->nbr, c->obs, c->jt, c->rows, c->lf_rows, c->nl,
+            seed, t, site, c->gid, usd, uad, c->accept, c->logpa, c->accepted_any);
+        KLAUNCH(c);
+    } else {
+        const size_t mtm_smem = (size_t)MTM_WARPS * ((1u << c->max_degree) - 1u) * (BT_MAX_D + 1) * sizeof(float);
+        mtm_select_kernel<false><<<(n_pix + MTM_WARPS - 1) / MTM_WARPS, MTM_WARPS * 32, mtm_smem, c->stream>>>(c->pr, c->fm,
+            n_pix, sp, c->D, c->L, K, c->max_degree, c->n_sites > 1, c->theta, c->nbr, c->obs, c->jt, c->rows, c->lf_rows, c->nl,
+            seed, t, site, c->gid, usd, uad, c->accept, c->logpa, c->accepted_any);
+        KLAUNCH(c);
+    }
     free_tmp(c, tmp);
     return 0;
 }

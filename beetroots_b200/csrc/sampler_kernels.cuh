@@ -351,11 +351,81 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Negative log weight of every candidate row (my_sampler.py:1017-1105) for graphs of degree <= 4: ONE THREAD PER ROW (all
+// lanes busy, where the warp-per-pixel kernel below idles 20 % of them at K + 1 = 51), everything in registers.  The
+// proposal log-density (utils.py:419-495) needs, per dimension, log sum_S sqrt(tau) m_S exp(-(x - mu_S)^2 tau m_S^2) over
+// the non-empty neighbour subsets S; since (x - mu_S) m_S = sum_{j in S} (x - theta_j), the exponent is
+// -tau (sum_{j in S} a_j)^2 with a_j = x - theta_j: 11 additions give all 15 subset sums, no means, no divisions.
+__global__ void __launch_bounds__(128)
+mtm_nl_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_pix, int D, int L, int K, int max_degree,
+              const float* __restrict__ theta, const int* __restrict__ nbr, const ObsConst* __restrict__ obs,
+              const float* __restrict__ cand_rows, const float* __restrict__ lf_rows, float* __restrict__ nl) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (long long)n_pix * (K + 1)) return;
+    const int i = (int)(row / (K + 1));
+    const int n = site_pix[i];
+    float x[BT_MAX_D], dummy[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[(size_t)row * D + d] : 0.f;
+    float val = lik_row<false>(fm, L, lf_rows + (size_t)row * L, nullptr, obs + (size_t)n * L, dummy);      // :1021-1025
+    if (pr.has_indicator) val += indicator_terms(pr, D, x, dummy);                                         // posterior.py:105-110
+    if (pr.has_spatial) {
+        // valid neighbours compacted to the front, in edge-list order
+        int nb[4], deg = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nb[j] = -1;
+        for (int j = 0; j < max_degree && j < 4; ++j) {
+            const int m = nbr[(size_t)n * max_degree + j];
+            if (m >= 0) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) if (jj == deg) nb[jj] = m;
+                ++deg;
+            }
+        }
+        if (deg == 0) { nl[row] = -INFINITY; return; }               // isolated pixel: empty logsumexp
+        const uint32_t nsub = (1u << deg) - 1u;
+        float sp = 0.f, total = 0.f;
+#pragma unroll
+        for (int d = 0; d < BT_MAX_D; ++d) {
+            if (d >= D) continue;
+            float a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = (j < deg) ? x[d] - theta[(size_t)nb[j] * D + d] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sp = fmaf(pr.tau[d] * a[j], a[j], sp);                              // posterior.py:96-103
+            // subset sums, index = mask - 1
+            float ssum[15];
+            ssum[0] = a[0]; ssum[1] = a[1]; ssum[2] = a[0] + a[1]; ssum[3] = a[2];
+            ssum[4] = a[0] + a[2]; ssum[5] = a[1] + a[2]; ssum[6] = ssum[2] + a[2]; ssum[7] = a[3];
+            ssum[8] = a[0] + a[3]; ssum[9] = a[1] + a[3]; ssum[10] = ssum[2] + a[3]; ssum[11] = a[2] + a[3];
+            ssum[12] = ssum[4] + a[3]; ssum[13] = ssum[5] + a[3]; ssum[14] = ssum[6] + a[3];
+            const float tau = pr.tau_prop[d], st = sqrtf(tau);
+            float e[15], mx = -INFINITY;                             // numba_logsumexp_stable, utils.py:390-416
+#pragma unroll
+            for (int q = 0; q < 15; ++q) {
+                e[q] = -tau * ssum[q] * ssum[q];
+                if ((uint32_t)q < nsub) mx = fmaxf(mx, e[q]);
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 15; ++q) {
+                const float m = (float)__popc((uint32_t)q + 1u);
+                if ((uint32_t)q < nsub) acc = fmaf(st * m, expf(e[q] - mx), acc);
+            }
+            total += logf(acc) + mx;
+        }
+        val += sp + total;           // chromatic factor 1 (l22:103-105) + proposal density (my_sampler.py:1093-1105)
+    }
+    nl[row] = val;
+}
+
 // weights, selection, accept (my_sampler.py:1017-1178): one warp per pixel, lanes stride over candidates.
 // Shared memory per warp: the means mu_S (and sizes m_S) of all 2^deg - 1 non-empty neighbour subsets, computed once
 // per pixel and reused by every candidate for the proposal log-density
 //   log q(x) = sum_d log sum_S sqrt(tau_d) m_S exp(-(x_d - mu_Sd)^2 tau_d m_S^2)          (utils.py:419-495)
 #define MTM_WARPS 4
+// NL_READY: nl_scratch already holds the negative log weights (mtm_nl_kernel below): selection / accept only
+template <bool NL_READY>
 __global__ void __launch_bounds__(MTM_WARPS * 32)
 mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_pix, int D, int L,
                   int K, int max_degree, int chromatic, float* __restrict__ theta,
@@ -372,6 +442,11 @@ mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ si
     const int n = site_pix[i];
     const int K1 = K + 1;
     const int nsub_max = (1 << max_degree) - 1;
+    float* nl = nl_scratch + (size_t)i * K1;
+    float mn = INFINITY;
+    if (NL_READY) {
+        for (int k = lane; k < K1; k += 32) mn = fminf(mn, nl[k]);
+    } else {
     float* mu = mtm_smem + (size_t)wib * nsub_max * (BT_MAX_D + 1);      // [nsub][D] then m_S in slot D
     // ---- neighbours (registers; loops are unrolled over BT_MAX_DEGREE with guards)
     const int* nb = nbr + (size_t)n * max_degree;
@@ -411,9 +486,7 @@ mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ si
         mu[sidx * (BT_MAX_D + 1) + BT_MAX_D] = m;
     }
     __syncwarp();
-    float* nl = nl_scratch + (size_t)i * K1;
     // ---- negative log weight of every candidate
-    float mn = INFINITY;
     for (int k = lane; k < K1; k += 32) {
         const size_t row = (size_t)i * K1 + k;
         float x[BT_MAX_D], dummy[BT_MAX_D];
@@ -459,6 +532,7 @@ mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ si
         nl[k] = val;
         mn = fminf(mn, val);
     }
+    }   // !NL_READY
     mn = warp_min(mn);
     __syncwarp();
     // ---- selection, ratio, accept.  The reference works with w_k = exp(-(nl_k - min nl)) in float64 (:1107-1114);
