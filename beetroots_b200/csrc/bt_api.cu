@@ -7,6 +7,8 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "common.cuh"
 #include "mlp_simt.cuh"
@@ -65,6 +67,10 @@ struct bt_ctx {
     bool snap_live = false;
     double* colsum = nullptr;
     int colsum_cap = 0;
+    // compaction of the pixels accepted during an MTM iteration (bt_mtm_finish)
+    int *acc_list = nullptr, *acc_count = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
     // on-device chain store (chain_kernels.cuh)
     float* chain = nullptr;
     int64_t chain_cap = 0, chain_len = 0;
@@ -152,7 +158,7 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
     tc3_free(c->tc3);
     void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
-                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl, c->chain, c->snap_theta, c->snap_nll, c->snap_grad, c->snap_lf, c->colsum};
+                    c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl, c->chain, c->snap_theta, c->snap_nll, c->snap_grad, c->snap_lf, c->colsum, c->acc_list, c->acc_count, c->cub_tmp};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -625,6 +631,16 @@ extern "C" int bt_pmala_site(bt_ctx* c, int site, double eps, double eta, double
     return 0;
 }
 
+// forward map of the candidate rows of one colour class: the n_pix x K proposals; ln f of the current values comes from
+// the per-pixel cache (see mtm_row in sampler_kernels.cuh)
+static int mtm_forward(bt_ctx* c, int n_pix, const int* sp, int K) {
+    if (run_mlp(c, c->rows, (int)((size_t)n_pix * K), c->lf_rows, nullptr)) return -1;
+    const long long tot = (long long)n_pix * c->L;
+    mtm_current_lf_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(n_pix, sp, c->L, K, c->lf_cache, c->lf_rows);
+    KLAUNCH(c);
+    return 0;
+}
+
 extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t, const float* cand_inject,
                            const float* usel_inject, const float* uacc_inject) {
     READY(c);
@@ -645,7 +661,7 @@ extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t,
     mtm_gen_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->pr, n_pix, sp, c->D, K, c->max_degree, c->theta,
         c->nbr, seed, t, site, c->gid, cd, c->rows);
     KLAUNCH(c);
-    if (run_mlp(c, c->rows, (int)M, c->lf_rows, nullptr)) { free_tmp(c, tmp); return -1; }
+    if (mtm_forward(c, n_pix, sp, K)) { free_tmp(c, tmp); return -1; }
     static const bool split_off = getenv("BT_MTM_NOSPLIT") != nullptr;
     if (c->max_degree <= 4 && !split_off) {
         // degree <= 4: weights by one thread per candidate row, then selection by one warp per pixel
@@ -670,10 +686,38 @@ extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t,
 extern "C" int bt_mtm_finish(bt_ctx* c, double alpha) {
     READY(c);
     CK(cudaSetDevice(c->device));
-    if (ensure_rows(c, c->N, true)) return -1;
-    if (run_mlp(c, c->theta, c->N, c->lf_rows, c->jac_rows)) return -1;
-    mtm_finish_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, c->N, c->D, c->L, c->max_degree, c->theta,
-        c->nbr, c->obs, c->lf_rows, c->jac_rows, c->nll_lik, c->grad_lik, c->lf_cache, c->v, (float)alpha, c->accepted_any);
+    static const bool no_compact = getenv("BT_MTM_FINISH_ALL") != nullptr;
+    if (no_compact) {                                    // reference behaviour: recompute the whole map
+        if (ensure_rows(c, c->N, true)) return -1;
+        if (run_mlp(c, c->theta, c->N, c->lf_rows, c->jac_rows)) return -1;
+        mtm_finish_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, c->N, c->D, c->L, c->max_degree, c->theta,
+            c->nbr, c->obs, c->lf_rows, c->jac_rows, c->nll_lik, c->grad_lik, c->lf_cache, c->v, (float)alpha, c->accepted_any);
+        KLAUNCH(c);
+        return 0;
+    }
+    // ordered list of the accepted pixels (deterministic: cub::DeviceSelect keeps the input order)
+    if (!c->acc_list) { CK(cudaMalloc(&c->acc_list, (size_t)c->N * sizeof(int))); CK(cudaMalloc(&c->acc_count, sizeof(int))); }
+    cub::CountingInputIterator<int> ids(0);
+    size_t need = 0;
+    CK(cub::DeviceSelect::Flagged(nullptr, need, ids, c->accepted_any, c->acc_list, c->acc_count, c->N, c->stream));
+    if (need > c->cub_tmp_bytes) {
+        if (c->cub_tmp) cudaFree(c->cub_tmp);
+        CK(cudaMalloc(&c->cub_tmp, need));
+        c->cub_tmp_bytes = need;
+    }
+    CK(cub::DeviceSelect::Flagged(c->cub_tmp, need, ids, c->accepted_any, c->acc_list, c->acc_count, c->N, c->stream));
+    c->launches++;
+    int n_acc = 0;
+    CK(cudaMemcpyAsync(&n_acc, c->acc_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_acc == 0) return 0;
+    if (ensure_rows(c, n_acc, true)) return -1;
+    gather_rows_kernel<<<(unsigned)(((size_t)n_acc * c->D + 255) / 256), 256, 0, c->stream>>>(c->theta, c->acc_list, n_acc, c->D, c->rows);
+    KLAUNCH(c);
+    if (run_mlp(c, c->rows, n_acc, c->lf_rows, c->jac_rows)) return -1;
+    mtm_finish_compact_kernel<<<(n_acc + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, n_acc, c->acc_list, c->D, c->L,
+        c->max_degree, c->theta, c->nbr, c->obs, c->lf_rows, c->jac_rows, c->nll_lik, c->grad_lik, c->lf_cache, c->v,
+        (float)alpha, c->accepted_any);
     KLAUNCH(c);
     return 0;
 }
@@ -993,7 +1037,7 @@ extern "C" int bt_mtm_optim_weights(bt_ctx* c, int site, int K, uint64_t seed, i
     mtm_gen_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->pr, n_pix, sp, c->D, K, c->max_degree, c->theta,
         c->nbr, seed, t, site, c->gid, cd, c->rows);
     KLAUNCH(c);
-    if (run_mlp(c, c->rows, (int)M, c->lf_rows, nullptr)) { free_tmp(c, tmp); return -1; }
+    if (mtm_forward(c, n_pix, sp, K)) { free_tmp(c, tmp); return -1; }
     mtm_optim_nl_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(c->pr, c->fm, n_pix, sp, c->D, c->L, K,
         c->max_degree, c->theta, c->nbr, c->obs, c->rows, c->lf_rows, c->nl);
     KLAUNCH(c);

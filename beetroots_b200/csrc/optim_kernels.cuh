@@ -64,10 +64,11 @@ __global__ void mtm_optim_nl_kernel(PriorDev pr, FmapDev fm, int n_pix, const in
     if (row >= (long long)n_pix * (K + 1)) return;
     const int i = (int)(row / (K + 1));
     const int n = site_pix[i];
+    const size_t r = mtm_row(i, (int)(row - (long long)i * (K + 1)), K, n_pix);
     float x[BT_MAX_D], dummy[BT_MAX_D];
 #pragma unroll
-    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[(size_t)row * D + d] : 0.f;
-    float val = lik_row<false>(fm, L, lf_rows + (size_t)row * L, nullptr, obs + (size_t)n * L, dummy);
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[r * D + d] : 0.f;
+    float val = lik_row<false>(fm, L, lf_rows + r * L, nullptr, obs + (size_t)n * L, dummy);
     if (pr.has_spatial) {
         float had[BT_MAX_D], lap[BT_MAX_D];
         neighbour_sums(theta, nbr + (size_t)n * max_degree, max_degree, D, x, had, lap);
@@ -112,6 +113,6 @@ __global__ void mtm_optim_select_kernel(int n_pix, const int* __restrict__ site_
     accept[n] = acc ? 1.f : 0.f;
     if (acc) {
         accepted_any[n] = 1;
-        for (int d = 0; d < D; ++d) theta[(size_t)n * D + d] = cand_rows[((size_t)i * (K + 1) + k_star) * D + d];
+        for (int d = 0; d < D; ++d) theta[(size_t)n * D + d] = cand_rows[((size_t)i * K + k_star) * D + d];
     }
 }

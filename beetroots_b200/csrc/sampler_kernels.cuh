@@ -282,6 +282,20 @@ __device__ __forceinline__ float smooth_indicator_draw(const PriorDev& pr, int d
     return (r[2] & 1u) ? hi + mag : lo - mag;                                         // :87-95
 }
 
+// Row layout of the candidate buffers (cand_rows, lf_rows) of one colour class: the n_pix x K proposals first, [i][k], then
+// the n_pix current values.  Only the proposals go through the forward map: ln f of a current value is already cached
+// per pixel (lf_cache) and is copied behind them (mtm_current_lf_kernel) -- one forward-map row in K + 1 saved.
+__device__ __forceinline__ size_t mtm_row(int i, int k, int K, int n_pix) {
+    return k < K ? (size_t)i * K + k : (size_t)n_pix * K + i;
+}
+__global__ void mtm_current_lf_kernel(int n_pix, const int* __restrict__ site_pix, int L, int K,
+                                      const float* __restrict__ lf_cache, float* __restrict__ lf_rows) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_pix * L) return;
+    const int i = (int)(idx / L), l = (int)(idx - (long long)i * L);
+    lf_rows[((size_t)n_pix * K + i) * L + l] = lf_cache[(size_t)site_pix[i] * L + l];
+}
+
 // candidate generation (sampler/utils/utils.py:274-349): thread per (pixel, k); slot K = current value
 __global__ void mtm_gen_kernel(PriorDev pr, int n_pix, const int* __restrict__ site_pix, int D, int K, int max_degree,
                                const float* __restrict__ theta, const int* __restrict__ nbr, uint64_t seed,
@@ -291,7 +305,7 @@ __global__ void mtm_gen_kernel(PriorDev pr, int n_pix, const int* __restrict__ s
     if (idx >= (long long)n_pix * (K + 1)) return;
     const int i = (int)(idx / (K + 1)), k = (int)(idx - (long long)i * (K + 1));
     const int n = site_pix[i];
-    float* out = cand_rows + (size_t)idx * D;
+    float* out = cand_rows + mtm_row(i, k, K, n_pix) * D;
     if (k == K) {                                                                     // my_sampler.py:1011-1015
         for (int d = 0; d < D; ++d) out[d] = theta[(size_t)n * D + d];
         return;
@@ -364,10 +378,11 @@ mtm_nl_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ site_p
     if (row >= (long long)n_pix * (K + 1)) return;
     const int i = (int)(row / (K + 1));
     const int n = site_pix[i];
+    const size_t r = mtm_row(i, (int)(row - (long long)i * (K + 1)), K, n_pix);
     float x[BT_MAX_D], dummy[BT_MAX_D];
 #pragma unroll
-    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[(size_t)row * D + d] : 0.f;
-    float val = lik_row<false>(fm, L, lf_rows + (size_t)row * L, nullptr, obs + (size_t)n * L, dummy);      // :1021-1025
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[r * D + d] : 0.f;
+    float val = lik_row<false>(fm, L, lf_rows + r * L, nullptr, obs + (size_t)n * L, dummy);                // :1021-1025
     if (pr.has_indicator) val += indicator_terms(pr, D, x, dummy);                                         // posterior.py:105-110
     if (pr.has_spatial) {
         // valid neighbours compacted to the front, in edge-list order
@@ -488,7 +503,7 @@ mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ si
     __syncwarp();
     // ---- negative log weight of every candidate
     for (int k = lane; k < K1; k += 32) {
-        const size_t row = (size_t)i * K1 + k;
+        const size_t row = mtm_row(i, k, K, n_pix);
         float x[BT_MAX_D], dummy[BT_MAX_D];
 #pragma unroll
         for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? cand_rows[row * D + d] : 0.f;
@@ -599,7 +614,7 @@ mtm_select_kernel(PriorDev pr, FmapDev fm, int n_pix, const int* __restrict__ si
         logpa[n] = log_rg;
         if (acc) {
             accepted_any[n] = 1;
-            const size_t row = (size_t)i * K1 + sel;
+            const size_t row = mtm_row(i, sel, K, n_pix);
             for (int d = 0; d < D; ++d) {
                 theta[(size_t)n * D + d] = cand_rows[row * D + d];                 // :1164-1168
                 jt[(size_t)n * D + d] = 0;                                         // :1174-1178
@@ -634,6 +649,35 @@ __global__ void mtm_finish_kernel(PriorDev pr, FmapDev fm, int N, int D, int L, 
                 const float g = nan_to_num(gl[d] + gp[d]);
                 v[(size_t)n * D + d] = alpha * v[(size_t)n * D + d] + (1.0f - alpha) * g * g;   // :1189-1195
             }
+        }
+    accepted_any[n] = 0;
+}
+
+// same on the compacted list of accepted pixels (row i of lf_rows / jac_rows belongs to pixel list[i]): pixels that kept
+// their value keep their cached likelihood terms, so only the accepted ones go through the forward map + Jacobian
+__global__ void mtm_finish_compact_kernel(PriorDev pr, FmapDev fm, int n_acc, const int* __restrict__ list, int D, int L,
+                                          int max_degree, const float* __restrict__ theta, const int* __restrict__ nbr,
+                                          const ObsConst* __restrict__ obs, const float* __restrict__ lf_rows,
+                                          const float* __restrict__ jac_rows, float* __restrict__ nll_lik,
+                                          float* __restrict__ grad_lik, float* __restrict__ lf_cache, float* __restrict__ v,
+                                          float alpha, uint8_t* __restrict__ accepted_any) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_acc) return;
+    const int n = list[i];
+    float gl[BT_MAX_D];
+    const float nll = lik_row<true>(fm, L, lf_rows + (size_t)i * L, jac_rows + (size_t)i * fm.T * L, obs + (size_t)n * L, gl);
+    nll_lik[n] = nll;
+    for (int l = 0; l < L; ++l) lf_cache[(size_t)n * L + l] = lf_rows[(size_t)i * L + l];
+    float x[BT_MAX_D], gp[BT_MAX_D];
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d) x[d] = (d < D) ? theta[(size_t)n * D + d] : 0.f;
+    prior_eval(pr, theta, nbr + (size_t)n * max_degree, max_degree, D, x, gp);
+#pragma unroll
+    for (int d = 0; d < BT_MAX_D; ++d)
+        if (d < D) {
+            grad_lik[(size_t)n * D + d] = gl[d];
+            const float g = nan_to_num(gl[d] + gp[d]);
+            v[(size_t)n * D + d] = alpha * v[(size_t)n * D + d] + (1.0f - alpha) * g * g;           // :1189-1195
         }
     accepted_any[n] = 0;
 }
@@ -784,5 +828,5 @@ __global__ void debug_scatter_cand_kernel(int n_pix, const int* site_pix, int D,
     const int d = (int)(idx % D);
     const long long ik = idx / D;
     const int k = (int)(ik % K), i = (int)(ik / K);
-    cand_full[((size_t)site_pix[i] * K + k) * D + d] = cand_rows[((size_t)i * (K + 1) + k) * D + d];
+    cand_full[((size_t)site_pix[i] * K + k) * D + d] = cand_rows[((size_t)i * K + k) * D + d];
 }
