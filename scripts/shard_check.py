@@ -22,6 +22,7 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 mlp = MLP_BF16_TC if mode == "bf16" else MLP_FP32
+NEXT = mode == "next"          # fp32 + the "next" rows: chain store, optimisation mode, regularisation-weight update
 prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K, use_next_nearest_neighbors=(mode == "fp32n8"))
 post = prob.posterior
 sdev = ShardedDevicePosterior(post, H, W, device=local, mlp_mode=mlp)
@@ -36,8 +37,36 @@ for t in range(1, 7):
     stats.append(a)
 th, v, j = sdev.get_state()
 terms = sdev.objective_terms()
+extra = {}
+if NEXT:
+    from beetroots_b200.mml import EBayesMMLELogRate
+    # (1) on-device chain store: three more iterations, each pushed; summaries gathered over the bands
+    sdev.chain_reserve(4)
+    sdev.chain_push()
+    for t in range(7, 10):
+        smp.generate_new_sample_pmala_rmsprop(t, post)
+        sdev.chain_push()
+    st = sdev.chain_stats(0, None, [10.0, 50.0, 90.0], want_var=True)
+    extra.update(chain=sdev.chain_get(), chain_mean=st["mean"], chain_var=st["var"], chain_lo=st["lo"], chain_hi=st["hi"])
+    # (2) optimisation mode: one MTM and one PMALA step (global argmin / global objective through all-reduce)
+    smp.stochastic = False
+    a_mtm = smp.generate_new_sample_mtm(10, post)
+    a_pm = smp.generate_new_sample_pmala_rmsprop(11, post)
+    extra.update(theta_opt=sdev.get_state()[0], opt_stats=np.array([a_mtm[0], float(a_pm[0])]),
+                 opt_objective=sdev.objective_terms()["objective"])
+    smp.stochastic = True
+    # (3) regularisation-weight update, then two sampling iterations with the new weights
+    opt = EBayesMMLELogRate(scale=1.0, N0=1, N1=+np.inf, dim=post.D * post.N, vmin=1e-8, vmax=1e8, homogeneity=2.0, exponent=0.8)
+    taus = []
+    for t in range(12, 14):
+        tau_t = smp.sample_regu_hyperparams(post, opt, t - 11)
+        post.prior_spatial.weights = tau_t * 1
+        sdev.update_spatial_weights(post.prior_spatial, post.prior_indicator)
+        taus.append(tau_t)
+        smp.generate_new_sample_mtm(t, post) if t % 2 == 0 else smp.generate_new_sample_pmala_rmsprop(t, post)
+    extra.update(taus=np.array(taus), theta_tau=sdev.get_state()[0])
 if int(os.environ.get("RANK", "0")) == 0:
-    np.savez(out, theta=th, v=v, j=j, stats=np.array(stats), objective=terms["objective"])
+    np.savez(out, theta=th, v=v, j=j, stats=np.array(stats), objective=terms["objective"], **extra)
     print("world", world, "accept/logpa per iteration", np.array(stats).round(4).tolist(), "objective", terms["objective"])
 if world > 1:
     dist.destroy_process_group()
