@@ -162,6 +162,8 @@ def run_ours(args):
     assert world == args.gpus or world == 1, (world, args.gpus)
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the ONE JSON line and nothing else: NCCL's own banner (NCCL_DEBUG=VERSION/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     H = W = args.size
     K = args.k_mtm
