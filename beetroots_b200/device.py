@@ -96,6 +96,7 @@ class DevicePosterior:
         self.site_keys = site_keys
         self.site_pixels = site_pixels      # list of np arrays (local pixel ids)
         self.max_degree = max_degree
+        self.has_spatial = self.has_indicator = True
         self._lib = L.load()
 
     # ------------------------------------------------------------------ construction
@@ -155,6 +156,7 @@ class DevicePosterior:
         lo = L.as_f64(pi.lower_bounds) if pi is not None else np.zeros(D)
         hi = L.as_f64(pi.upper_bounds) if pi is not None else np.zeros(D)
         delta = float(pi.indicator_margin_scale) if pi is not None else 1.0
+        self.has_spatial, self.has_indicator = ps is not None, pi is not None
         L.check(self._lib.bt_upload_priors(self._ctx, int(ps is not None), L.dptr(tau), L.dptr(tau0), int(pi is not None),
                                            L.dptr(lo), L.dptr(hi), delta), "bt_upload_priors")
 
@@ -227,9 +229,19 @@ class DevicePosterior:
         out = np.zeros(2 + 2 * self.D)
         ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
         L.check(self._lib.bt_objective_terms(self._ctx, L.dptr(ow, C.c_uint8), L.dptr(out)), "bt_objective_terms")
+        return self._dict_objective(out)
+
+    def _dict_objective(self, out) -> dict:
+        """Same keys and types as the reference (posterior.py:300-330): numpy scalars (``MySaver.initialize_memory`` reads
+        ``v.shape`` of every entry, my_saver.py:57-58), prior entries only when the prior exists."""
         D = self.D
-        return {"nll": np.float64(out[0]), "nl_prior_spatial": out[1:1 + D].copy(),
-                "nl_prior_indicator": out[1 + D:1 + 2 * D].copy(), "objective": float(out[1 + 2 * D])}
+        d = {"nll": np.float64(out[0])}
+        if self.has_spatial:
+            d["nl_prior_spatial"] = np.array(out[1:1 + D], dtype=np.float64)
+        if self.has_indicator:
+            d["nl_prior_indicator"] = np.array(out[1 + D:1 + 2 * D], dtype=np.float64)
+        d["objective"] = np.float64(out[1 + 2 * D])
+        return d
 
     def spatial_prior_unweighted(self, owned=None) -> np.ndarray:
         """prior_spatial.neglog_pdf(Theta, idx_pix=arange(N), with_weights=False) -> (D,)

@@ -199,11 +199,10 @@ class ShardedDevicePosterior:
         d = self.local.objective_terms(self._owned)
         if self.world == 1:
             return d
-        vec = np.concatenate([[d["nll"]], d["nl_prior_spatial"], d["nl_prior_indicator"], [d["objective"]]])
-        vec = self._allreduce(vec)
         D = self.D
-        return {"nll": np.float64(vec[0]), "nl_prior_spatial": vec[1:1 + D], "nl_prior_indicator": vec[1 + D:1 + 2 * D],
-                "objective": float(vec[-1])}
+        vec = np.concatenate([[d["nll"]], d.get("nl_prior_spatial", np.zeros(D)), d.get("nl_prior_indicator", np.zeros(D)),
+                              [d["objective"]]])
+        return self.local._dict_objective(self._allreduce(vec))
 
     # ---- optimisation mode: same steps as DevicePosterior, with the halo exchange and the global reductions in between
     def optim_pmala_step(self, eps, eta, alpha, seed, t, z=None):

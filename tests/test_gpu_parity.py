@@ -201,6 +201,8 @@ def test_sample_runs_with_saver_protocol(lib):
             self.memory["list_Theta"].append(Theta.copy())
             self.memory["list_objective"].append(dict_objective["objective"])
             assert set(dict_objective) == {"nll", "nl_prior_spatial", "nl_prior_indicator", "objective"}
+            # what the reference's MySaver does with every entry (my_saver.py:57-58) and what sample() asserts (:468)
+            assert all(hasattr(v, "shape") for v in dict_objective.values()) and isinstance(dict_objective["objective"], float)
             assert kw["rng_state_array"].shape == (32,)
 
         def check_need_to_update_memory(self, t):
