@@ -61,6 +61,10 @@ struct Tc3Sched {
     int trace_i0;
     int dbg_flags;                 // debug: 1 = every chunk advances the ring by 16 KB, 2 = one MMA issuer; knock-outs: 4 = no activation math, 8 = no MMAs, 256 = no weight copies
     uint8_t* dump;                 // debug: activation buffers of both CTAs after the last tile (BT_TC3_DUMP=file)
+    int pre_kb;                    // > 0: K-blocks [0, pre_kb) of every tile come ready-made from the pre-pass kernel (mlp_pre.cuh)
+    int pre_feats;                 // number of features they hold (= inputs of the first block this kernel evaluates)
+    int pre_blocks;                // leading blocks evaluated by the pre-pass
+    const uint8_t* pre_img;        // [pair-tile][CTA][pre_kb][8 KB]: the exact shared-memory image of those K-blocks
 };
 struct Tc3Net {
     bool ready = false;
@@ -76,13 +80,15 @@ static inline void tc3_free(Tc3Net& t) {
 }
 
 static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t* block_new, const double* const* weights,
-                            const double* const* biases, const double* w_out, int n_out, double out_scale) {
+                            const double* const* biases, const double* w_out, int n_out, double out_scale, int skip = 0) {
     t.ready = false;
     if (n_blocks + 1 > TC_MAX_LAYERS || n_out > 32 || n_feat0 > 64 || n_blocks < 1) return 0;
+    if (skip < 0 || skip > n_blocks - 2) return 0;
     Tc3Sched& s = t.sched;
     memset(&s, 0, sizeof s);
     s.n_out = n_out;
-    s.n_ready = n_blocks + 1;
+    s.n_ready = n_blocks - skip + 1;
+    s.pre_blocks = skip;
     s.ready_count[0] = 2;                        // one arrival per CTA (the epilogue warps meet at a named barrier first)
     const int og = (n_out + 7) / 8;
     // what every streamed row is: layer (-1 = output layer), row of that layer, K window [klo, khi)
@@ -97,6 +103,9 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
     for (int l = 0; l < n_blocks; ++l) {
         const int in = w, nnew = block_new[l];
         if (l == n_blocks - 2) layer_in_of_last_minus_1 = in;
+        if (l < skip) { prev_in = in; w += nnew; continue; }       // evaluated by the pre-pass kernel
+        if (l == skip && skip > 0) { s.pre_feats = in; s.pre_kb = (in + TC_BK - 1) / TC_BK; }
+        const int lrel = l - skip;
         const int n_mt = (nnew + 255) / 256;
         for (int mt = 0; mt < n_mt; ++mt) {
             if (nu >= TC3_MAX_UNITS - 1) return 0;
@@ -114,11 +123,11 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
             unit_mt[nu] = mt;
             U.k16_begin = 0;
             U.k16_end = (short)((in + 15) / 16);
-            U.new_k16 = (short)(l == 0 ? 0 : prev_in / 16);
-            U.dep = (short)l;
+            U.new_k16 = (short)(lrel == 0 ? 0 : prev_in / 16);
+            U.dep = (short)lrel;
             U.sp = (short)(nu & 1);
             U.flags = fold ? TC3_F_HOLD : 0;
-            U.ready_idx = (short)(l + 1);
+            U.ready_idx = (short)(lrel + 1);
             U.two = (short)(((U.k16_end + 3) / 4) >= 2);
             U.gelu_lane0[0] = (short)(o * 8);
             U.gelu_lane0[1] = 0;
@@ -139,7 +148,7 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
             if (U.groups[0] > 16 || U.groups[1] > 16) return 0;
             U.feat0[0] = in + 256 * mt;
             U.feat0[1] = in + 256 * mt + U.gelu_rows[0];
-            s.ready_count[l + 1] += (U.gelu_rows[0] > 0) + (U.gelu_rows[1] > 0);   // one arrival per CTA that produces features
+            s.ready_count[lrel + 1] += (U.gelu_rows[0] > 0) + (U.gelu_rows[1] > 0);   // one arrival per CTA that produces features
             for (int c = 0; c < 2; ++c) {
                 std::vector<RowSrc> rs((size_t)U.groups[c] * 8, RowSrc{-2, 0, 0, 0});
                 if (c == 0 && fold) for (int r = 0; r < n_out; ++r) rs[r] = RowSrc{-1, r, 0, in};
@@ -162,7 +171,7 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
         U.k16_begin = (short)(folded ? in_last / 16 : 0);
         U.k16_end = (short)((n_feat + 15) / 16);
         U.new_k16 = (short)(in_last / 16);
-        U.dep = (short)n_blocks;
+        U.dep = (short)(n_blocks - skip);
         U.sp = (short)(folded ? s.U[nu - 1].sp : (nu & 1));
         U.flags = (short)(TC3_F_FINAL | (folded ? TC3_F_CONT : 0));
         U.ready_idx = -1;
@@ -179,7 +188,8 @@ static inline int tc3_build(Tc3Net& t, int n_feat0, int n_blocks, const int32_t*
     }
     {
         int last0 = 0;
-        for (int u = 0; u < nu; ++u) if (s.U[u].k16_begin < 4) last0 = u;   // reads K-block 0
+        const int k16_in = 4 * (s.pre_kb > 0 ? s.pre_kb : 1);
+        for (int u = 0; u < nu; ++u) if (s.U[u].k16_begin < k16_in) last0 = u;   // reads the K-block(s) holding the tile's inputs
         s.U[last0].flags |= TC3_F_PUB;
     }
     s.n_units = nu;
@@ -392,7 +402,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_wait_f(uint32_t bar, uint32_t parity, bool spin) {
     if (spin) mbar_spin(bar, parity); else mbar_wait(bar, parity);
 }
-template <int S, int DBG>   // DBG: 0 = production, 1 = runtime debug flags / timelines, > 1 = these knock-out flags compiled in
+// PRE: the first sch.pre_kb K-blocks of every tile are copied from sch.pre_img (written by the pre-pass kernel) instead of
+// being computed here; the schedule then starts at block sch.pre_blocks
+template <int S, int DBG, bool PRE = false>   // DBG: 0 = production, 1 = runtime debug flags / timelines, > 1 = these knock-out flags compiled in
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ rows, int M, float* __restrict__ lf,
                float* __restrict__ jac) {
@@ -625,13 +637,32 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
         const int lane_g = qd * 32 + lane;
         uint32_t nfull0 = 0, nfull1 = 0, tcount_e = 0;
         float feat[TC3_FPT], x0_cur;
+        uint4 pv[3];                                                  // PRE: my 3 x 16 B of the next tile's input K-blocks
+        const int pre_n16 = PRE ? sch.pre_kb * (TC_KB_BYTES / 16) : 0;  // 16-byte words per CTA per tile (<= 1536)
+        auto load_pre = [&](int pt_) {
+            const uint4* src = reinterpret_cast<const uint4*>(sch.pre_img) + ((size_t)pt_ * 2 + crank) * (size_t)pre_n16;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int idx = t512 + 512 * q;
+                pv[q] = idx < pre_n16 ? __ldg(src + idx) : make_uint4(0, 0, 0, 0);
+            }
+        };
         uint32_t pub_parity = 0;
         auto publish_inputs = [&]() {
             const uint32_t parity = pub_parity;
+            if (PRE) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int idx = t512 + 512 * q;
+                    if (idx < pre_n16)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_s + (uint32_t)idx * 16u), "r"(pv[q].x), "r"(pv[q].y), "r"(pv[q].z), "r"(pv[q].w) : "memory");
+                }
+            } else {
 #pragma unroll
             for (int qf = 0; qf < TC3_FPT; ++qf) {
                 const int f = fg + 8 * qf;
                 if (f < net.F0) sts_bf16(act_s + sw128_offset((uint32_t)pcol, (uint32_t)f), feat[qf]);
+            }
             }
             if (fg == 0)
                 asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(x0_leader + (parity * 128u + (uint32_t)gcol_p) * 4u), "f"(x0_cur) : "memory");
@@ -640,7 +671,8 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
         if (pt0 < n_ptiles) {
             float xf0[BT_MAX_D + 1];
             tc_load_column(fm, rows, M, pt0 * P2 + pp, xf0);
-            tc3_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, pt0 * P2 + pp < M, xf0, feat);
+            if (PRE) load_pre(pt0);
+            else tc3_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, pt0 * P2 + pp < M, xf0, feat);
             x0_cur = xf0[0];
             publish_inputs();
             asm volatile("bar.sync 2, 512;" ::: "memory");
@@ -669,7 +701,8 @@ mlp_tc3_kernel(Tc3Sched sch, NetDev net, FmapDev fm, const float* __restrict__ r
                 const float b = gelu_live ? __ldg(sch.bias + kabs) : 0.f;
                 const bool pub = (U.flags & TC3_F_PUB) && has_next;
                 if (pub) {                                           // features of the next tile, while this unit's MMAs run
-                    tc3_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, row_n < M, xf_n, feat);
+                    if (PRE) load_pre(pt + pt_step);
+                    else tc3_poly_feats(pexp_s, pmean_s, pistd_s, net.F0, fg, ps, ptin, row_n < M, xf_n, feat);
                     x0_cur = xf_n[0];
                 }
 #if TC3_GATE
@@ -880,6 +913,15 @@ static inline int tc3_launch(Tc3Net& t, const FmapDev& fm, const NetDev& net, co
     else if (S == 1 && ko == 268) TC3_LAUNCH(1, 268);
     else if (S == 1 && ko == 260) TC3_LAUNCH(1, 260);
     else if (S == 1 && ko == 1024) TC3_LAUNCH(1, 1024);   // no generic->async proxy fence after the activation stores (results invalid)
+    else if (t.sched.pre_kb > 0) {
+        if (t.sched.pre_kb > 3 || !t.sched.pre_img) return -7;
+        err = S == 1 ? cudaFuncSetAttribute(mlp_tc3_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes)
+                     : cudaFuncSetAttribute(mlp_tc3_kernel<4, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes);
+        if (err == cudaSuccess) {
+            if (S == 1) mlp_tc3_kernel<1, 0, true><<<g, TC3_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
+            else        mlp_tc3_kernel<4, 0, true><<<g, TC3_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac);
+        }
+    }
     else if (S == 1) { if (use_dbg) TC3_LAUNCH(1, 1); else TC3_LAUNCH(1, 0); }
     else             { if (use_dbg) TC3_LAUNCH(4, 1); else TC3_LAUNCH(4, 0); }
 #undef TC3_LAUNCH

@@ -210,7 +210,8 @@ int bt_chain_get(bt_ctx* ctx, int64_t first, int64_t count, double* out);
 int bt_chain_stats(bt_ctx* ctx, int64_t first, int64_t count, int n_q, const double* percentiles, double* mean,
                    double* var, double* q_lo, double* q_hi, double* q_frac);
 
-/* which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 3 = pair kernel (default),
+/* which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 4 = pair kernel fed by the pre-pass
+ * kernel for the leading small blocks (default), 3 = pair kernel alone,
  * 1 = single-CTA kernel (fallback for shapes the pair kernel does not take), 2 = first cta_group::2 kernel, 0 = none. */
 int bt_mlp_kernel_variant(bt_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */

@@ -416,15 +416,16 @@ def test_tensor_core_variants_agree(lib):
         "lik = M.MixingModelsLikelihood(fm, 4, L, Mr, np.ones((Mr, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)), a1=np.ones((1, L)))\n"
         "dev = DevicePosterior.from_posterior(M.Posterior(4, L, Mr, lik, None, None), mlp_mode=MLP_BF16_TC)\n"
         "out = dev.forward_map(th, compute_derivatives=True)\n"
-        "np.savez(sys.argv[1], lf=out['log_f_Theta'], jac=out['grad_log_f_Theta'])\n"
+        "lf1 = dev.forward_map(th)['log_f_Theta']\n"
+        "np.savez(sys.argv[1], lf=out['log_f_Theta'], jac=out['grad_log_f_Theta'], lf1=lf1)\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     import tempfile
     outs = []
     with tempfile.TemporaryDirectory() as tmp:
-        for variant in ("1", "2", "3", "3"):
+        for variant in ("1", "2", "3", "3", "4", "4"):
             path = os.path.join(tmp, f"v{variant}_{len(outs)}.npz")
             env = dict(os.environ, BT_TC_VARIANT=variant)
-            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=150)
             assert r.returncode == 0, r.stderr[-2000:]
             outs.append(dict(np.load(path)))
     assert np.array_equal(outs[0]["lf"], outs[1]["lf"])
@@ -432,6 +433,14 @@ def test_tensor_core_variants_agree(lib):
     assert np.array_equal(outs[2]["lf"], outs[3]["lf"]) and np.array_equal(outs[2]["jac"], outs[3]["jac"])   # deterministic
     assert np.abs(outs[2]["lf"] - outs[0]["lf"]).max() < 5e-3
     assert np.abs(outs[2]["jac"] - outs[0]["jac"]).max() < 5e-3 * max(1.0, np.abs(outs[0]["jac"]).max())
+    # 4 = pair kernel fed by the pre-pass (leading blocks by warp-level MMAs, other summation order): same bound,
+    # deterministic, and the primal does not depend on whether tangent columns ride along (one function of theta)
+    assert np.array_equal(outs[4]["lf1"], outs[5]["lf1"]) and np.array_equal(outs[4]["jac"], outs[5]["jac"])
+    for o in (outs[2], outs[4]):
+        assert np.array_equal(o["lf1"], o["lf"])
+    assert not np.array_equal(outs[4]["lf1"], outs[2]["lf1"])     # (the pre-pass really ran)
+    assert np.abs(outs[4]["lf1"] - outs[2]["lf1"]).max() < 5e-3
+    assert np.abs(outs[4]["jac"] - outs[2]["jac"]).max() < 5e-3 * max(1.0, np.abs(outs[2]["jac"]).max())
 
 
 @pytest.mark.parametrize("arch,env", [
@@ -444,6 +453,7 @@ def test_tensor_core_variants_agree(lib):
     ((7, 0.5, 5), {}),                                    # shallow network: every block is a "small" unit
     ((6, 1.0, 7), {}),                                    # legacy dense architecture: widths double, last block = 3 units
     ((9, 0.5, 3), {}),
+    ((10, 0.5, 10), {"BT_TC_VARIANT": "4"}),              # leading blocks by the pre-pass kernel (the default)
 ])
 def test_pair_kernel_schedules_and_architectures(lib, arch, env):
     """The unit schedule of the default tensor-core kernel (mlp_tc3.cuh: folding, replication, chunk width, ring
@@ -463,7 +473,7 @@ def test_pair_kernel_schedules_and_architectures(lib, arch, env):
         "fm = M.NeuralNetworkApprox(net, {'kappa': None, 'P': None, 'radm': None, 'Avmax': None, 'angle': -1.5})\n"
         "lik = M.MixingModelsLikelihood(fm, 4, L, 8, np.ones((8, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)), a1=np.ones((1, L)))\n"
         "dev = DevicePosterior.from_posterior(M.Posterior(4, L, 8, lik, None, None))\n"
-        "assert dev.mlp_kernel_variant() == 3, dev.mlp_kernel_variant()\n"
+        "assert dev.mlp_kernel_variant() == %d, dev.mlp_kernel_variant()\n"
         "worst = 0.0\n"
         "for Mr, jac in ((1, False), (257, True), (20011, False), (5003, True)):\n"
         "    th = np.random.default_rng(Mr).uniform(-1.5, 1.5, size=(Mr, 4))\n"
@@ -473,9 +483,11 @@ def test_pair_kernel_schedules_and_architectures(lib, arch, env):
         "    if jac: e = max(e, np.abs(out['grad_log_f_Theta'] - ref['grad_log_f_Theta']).max() / max(1.0, np.abs(ref['grad_log_f_Theta']).max()))\n"
         "    worst = max(worst, float(e))\n"
         "print('WORST', worst)\n"
-    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n_out, n_layers, growing)
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BT_TC_VARIANT="3", **env), capture_output=True,
-                       text=True, timeout=300)
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n_out, n_layers, growing,
+         int(env.get("BT_TC_VARIANT", "3")))
+    full_env = dict(os.environ, BT_TC_VARIANT="3")
+    full_env.update(env)
+    r = subprocess.run([sys.executable, "-c", code], env=full_env, capture_output=True, text=True, timeout=150)
     assert r.returncode == 0, r.stderr[-2000:]
     worst = float(r.stdout.strip().split("WORST")[-1])
     assert worst < 4e-2, worst            # bf16 operands, fp32 accumulation: ~1e-2 in ln f on the reference architecture
