@@ -266,7 +266,9 @@ def run_ours(args):
     achieved = (mlp_rows * flops_row / (mlp_ms / 1000.0)) / 1e12 if mlp_ms > 0 else None
     traffic = None
     try:        # DRAM bytes per launch from the committed ncu --set full capture (per forward row x rows per launch)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_mlp_tc_traffic.json")))
+        # pre-pass + pair kernel (variant 4, the default) or the pair kernel alone: each has its own committed capture
+        v4 = sdev.local.mlp_kernel_variant() == 4
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01e_forward_map_traffic.json" if v4 else "r01_mlp_tc_traffic.json")))
         if mode == MLP_BF16_TC and mlp_launches:
             traffic = tj["dram_bytes_per_row"] * mlp_rows / mlp_launches
     except Exception:
@@ -287,7 +289,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                      "algorithmic_flops_per_launch": flops_row * mlp_rows / mlp_launches if mlp_launches else None,
-                     "kernel": "forward-map MLP", "peak_source": peak_src,
+                     "kernel": "forward-map MLP (pre-pass + pair kernel)" if (mode == MLP_BF16_TC and sdev.local.mlp_kernel_variant() == 4) else "forward-map MLP", "peak_source": peak_src,
                      "rows": int(mlp_rows), "launches": int(mlp_launches), "kernel_ms": mlp_ms,
                      "share_of_step": mlp_ms / ms if ms > 0 else None,
                      "pixel_candidate_evals_per_s_per_gpu": mlp_rows / (mlp_ms / 1000.0) if mlp_ms > 0 else None},
