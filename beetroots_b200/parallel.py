@@ -282,10 +282,13 @@ class ShardedDevicePosterior:
         own = local_arr[self.plan.owned > 0]
         sizes = [(band_rows(self.plan.H, self.world, r)[1] - band_rows(self.plan.H, self.world, r)[0]) * self.plan.W
                  for r in range(self.world)]
-        mine = torch.as_tensor(np.ascontiguousarray(own), device=self.dev)
-        outs = [torch.empty((s,) + tuple(own.shape[1:]), dtype=mine.dtype, device=self.dev) for s in sizes]
+        # bands may differ by one row: gather equal-sized (zero-padded) pieces and trim, which every backend supports
+        smax = max(sizes)
+        mine = torch.zeros((smax,) + tuple(own.shape[1:]), dtype=torch.as_tensor(own).dtype, device=self.dev)
+        mine[:own.shape[0]] = torch.as_tensor(np.ascontiguousarray(own), device=self.dev)
+        outs = [torch.empty_like(mine) for _ in sizes]
         self.dist.all_gather(outs, mine)
-        return torch.cat(outs, 0).cpu().numpy()
+        return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0).cpu().numpy()
 
     def get_state(self, want_v=True, want_j=True):
         th, v, j = self.local.get_state(want_v, want_j)

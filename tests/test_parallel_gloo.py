@@ -100,3 +100,66 @@ def test_halo_exchange_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, port, 7, 4, 3, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert np.load(tmp_path / f"ok{r}.npy")[0]
+
+
+# ---- the global reductions of the "next" rows (regularisation-weight update, optimisation-mode MTM, chain gather) --------
+def _reduction_worker(rank, world, port, H, W, out_dir):
+    """Every rank evaluates ITS band with the float64 oracle on the LOCAL graph (local_posterior) and the sharded host
+    code (ShardedDevicePosterior._allreduce / _gather_owned, the code the NCCL path runs) combines them; the result
+    must equal the oracle on the full map."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from beetroots_b200.parallel import ShardedDevicePosterior
+    from oracle import posterior as OP
+    D, L, K = 4, 3, 5
+    N = H * W
+    X, Y = np.repeat(np.arange(H), W), np.tile(np.arange(W), H)
+    sp = M.L22DiscreteGradSpatialPrior(D, N, X, Y, None, False, np.array([10.0, 1.0, 2.0, 4.0]))
+    lik = M.MixingModelsLikelihood(None, D, L, N, np.ones((N, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)), a1=np.ones((1, L)))
+    post = M.Posterior(D, L, N, lik, sp, None)
+    rng = np.random.default_rng(7)                                   # same stream on every rank
+    theta = rng.standard_normal((N, D))
+    cand = rng.standard_normal((N, K, D))
+    chain = rng.standard_normal((6, N, D))
+    nbr = M.build_neighbor_table(sp.list_edges, N, 4)
+    plan = make_band_plan(H, W, world, rank)
+    lp, sites = local_posterior(post, plan)
+    gid = plan.local_global_id
+    nbl = M.build_neighbor_table(lp.prior_spatial.list_edges, plan.n_local, 4)
+    sh = object.__new__(ShardedDevicePosterior)                      # the host logic without a CUDA context
+    sh.torch, sh.dist, sh.world, sh.rank, sh.plan, sh.dev = torch, dist, world, rank, plan, torch.device("cpu")
+    sh.N, sh.D, sh.L = N, D, L
+    th_loc = theta[gid]
+    ok = True
+    # (1) potential of the regularisation-weight update: 1/2 sum_n sum_{i in V_n} (theta_n - theta_i)^2 over OWNED pixels
+    had_loc, _ = OP.spatial_sums(th_loc, nbl)
+    g_loc = 0.5 * (had_loc * (plan.owned > 0)[:, None]).sum(axis=0)
+    had, _ = OP.spatial_sums(theta, nbr)
+    ok &= bool(np.allclose(sh._allreduce(g_loc), 0.5 * had.sum(axis=0), rtol=1e-12))
+    # (2) optimisation-mode MTM: per-candidate column sums over the owned pixels of a colour class, argmin after all-reduce
+    for s, loc in sites.items():
+        had_c, _ = OP.spatial_sums(th_loc, nbl, loc, cand[gid[loc]])           # (n_loc, K, D)
+        col_loc = (sp.weights * had_c).sum(-1).sum(axis=0)                      # (K,)
+        glob = sp.dict_sites[s]
+        had_g, _ = OP.spatial_sums(theta, nbr, glob, cand[glob])
+        col = (sp.weights * had_g).sum(-1).sum(axis=0)
+        red = sh._allreduce(col_loc)
+        ok &= bool(np.allclose(red, col, rtol=1e-12)) and int(np.argmin(red)) == int(np.argmin(col))
+    # (3) per-pixel arrays and the stored chain come back in global pixel order
+    ok &= bool(np.array_equal(sh._gather_owned(th_loc), theta))
+    jj = np.arange(N * D, dtype=np.int32).reshape(N, D)                      # the RMSProp counters travel as int32
+    got = sh._gather_owned(jj[gid])
+    ok &= got.dtype == np.int32 and bool(np.array_equal(got, jj))
+    ok &= bool(np.array_equal(sh._gather_owned(theta[gid, 0]), theta[:, 0]))   # 1-D per-pixel arrays (objectives, accept)
+    ch = np.swapaxes(sh._gather_owned(np.ascontiguousarray(np.swapaxes(chain[:, gid], 0, 1))), 0, 1)
+    ok &= bool(np.array_equal(ch, chain))
+    np.save(os.path.join(out_dir, f"red{rank}.npy"), np.array([ok]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_global_reductions_of_the_next_rows_gloo(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_reduction_worker, args=(world, port, 9, 5, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.load(tmp_path / f"red{r}.npy")[0]
