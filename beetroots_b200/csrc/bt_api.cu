@@ -264,8 +264,8 @@ extern "C" int bt_upload_network(bt_ctx* c, int n_in, int order, int n_feat0, co
         int skip = 0, w = n_feat0;
         while (skip < n_blocks - 2 && skip < 4 && w + block_new[skip] <= 3 * TC_BK) { w += block_new[skip]; ++skip; }
         // Only the shape class this path has been validated on (tests/test_gpu_parity.py): four leading blocks, output layer
-        // small enough to be folded into the last hidden unit.  A 32-line network (output layer as a unit of its own) was
-        // seen to dead-lock with the pre-pass schedule; everything else keeps the plain pair kernel until that is understood.
+        // folded into the last hidden unit, at most 16 lines.  The 32-line variant of the reference architecture did not
+        // finish with the shortened schedule (cause open); everything else keeps the plain pair kernel.
         if (skip == 4 && n_out <= 16) tc3_build(c->tc3p, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, LOGE10, skip);
         if (c->tc3p.ready && !(c->tc3p.sched.U[c->tc3p.sched.n_units - 1].flags & TC3_F_CONT)) tc3_free(c->tc3p);
         preb_free(c->preb);
