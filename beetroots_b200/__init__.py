@@ -9,5 +9,6 @@ from .modelling import (L22DiscreteGradSpatialPrior, MixingModelsLikelihood, Neu
 from .network import DenseMLPWeights, synthetic_weights  # noqa: F401
 from .device import MLP_BF16_TC, MLP_FP32, DevicePosterior  # noqa: F401
 from .sampler import B200Sampler, MySamplerParams  # noqa: F401
+from .saver import ChainSaver  # noqa: F401
 
 __version__ = "0.1.0"

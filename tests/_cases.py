@@ -70,3 +70,20 @@ def slice_noise(noise, post):
     for s, idx in post.dict_sites.items():
         out[s] = {k: np.asarray(v, dtype=np.float64)[idx] for k, v in noise[s].items()}
     return out
+
+
+# ---- deterministic inputs for the saver golden (tests/golden/make_golden_saver.py and tests/test_host.py) ----
+class Pow10Scaler:
+    def from_scaled_to_lin(self, x):
+        return 10.0 ** x
+
+
+def saver_inputs(t, N=5, D_s=2, L=2):
+    rng = np.random.default_rng(100 + t)
+    return dict(Theta=rng.standard_normal((N, D_s)),
+                forward_map_evals={"log_f_Theta": rng.standard_normal((N, L)), "grad_log_f_Theta": np.zeros((N, D_s, L))},
+                nll_utils={"nll": np.float64(rng.uniform()), "nll_au": np.zeros((N, L)), "m_a": rng.standard_normal((N, L))},
+                dict_objective={"nll": np.float64(t), "nl_prior_spatial": rng.uniform(size=D_s), "objective": np.float64(2.0 * t)},
+                additional_sampling_log={"v": rng.uniform(size=(N, D_s)), "type_t": t % 2, "accepted_t": 0.25 * t,
+                                         "log_proba_accept_t": -1.0 * t},
+                rng=(np.arange(32, dtype=np.uint8) + t, np.arange(32, dtype=np.uint8)[::-1] + t))

@@ -239,3 +239,38 @@ def test_sample_control_flow_optimisation_mode():
     # saved objectives 9, 8, 8.5, 7, 7, 6 at t = 1..6; burn-in t = 1; improvements at t = 2 (8 < inf), 4 (7), 6 (6)
     assert [c[1] for c in dev.calls if c[0] == "mc_snapshot"] == [2, 4, 6]
     assert [c[1] for c in dev.calls if c[0] == "mc_pvalues"] == [7, 8, 9, 10, 11]
+
+
+def test_chain_saver_matches_reference_saver_golden(tmp_path):
+    """beetroots_b200.saver.ChainSaver against the memory batches of the UNMODIFIED reference MySaver
+    (tests/golden/make_golden_saver.py): same dataset names, shapes, slots and values; npz back end round-trips."""
+    from _cases import Pow10Scaler as Pow10, saver_inputs as inputs
+    from beetroots_b200.saver import ChainSaver
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "saver_golden.npz"))
+    sv = ChainSaver(5, 3, 2, 2, Pow10(), results_path=str(tmp_path / "out"), batch_size=3, freq_save=2,
+                    save_forward_map_evals=True, list_idx_sampling=[0, 2])
+    sv._h5py = lambda: None                                               # force the npz back end whatever is installed
+    batches, T = [], 12
+    for t in range(1, T + 1):
+        x = inputs(t)
+        kw = {k: x[k] for k in ("Theta", "forward_map_evals", "nll_utils", "dict_objective", "additional_sampling_log")}
+        if sv.memory == {}:
+            sv.initialize_memory(T, t, **kw)
+            sv.update_memory(t, rng_state_array=x["rng"][0], rng_inc_array=x["rng"][1], **kw)
+        elif sv.check_need_to_update_memory(t):
+            sv.update_memory(t, rng_state_array=x["rng"][0], rng_inc_array=x["rng"][1], **kw)
+        if sv.check_need_to_save(t):
+            batches.append({k: v.copy() for k, v in sv.memory.items()})
+            sv.save_to_file()
+    assert len(batches) == int(g["n_batches"]) == 2
+    for b, mem in enumerate(batches):
+        ref_keys = {k.split("__", 1)[1] for k in g.files if k.startswith(f"b{b}__")}
+        assert set(mem) == ref_keys
+        for k, v in mem.items():
+            r = g[f"b{b}__{k}"]
+            assert v.shape == r.shape and v.dtype == r.dtype, k
+            np.testing.assert_array_equal(v, r, err_msg=k)
+    sv.save_additional([np.ones((5, 2)), np.zeros(5)], ["clppd", "p-values-llh"])
+    z = np.load(tmp_path / "out" / "mc_chains.npz")
+    assert z["list_Theta"].shape == (6, 5, 2) and z["clppd"].shape == (5, 2)
+    np.testing.assert_array_equal(z["list_Theta"], np.concatenate([g["b0__list_Theta"], g["b1__list_Theta"]], 0))
