@@ -16,6 +16,7 @@
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
 #include "mlp_tc3.cuh"
+#include "mlp_tc4.cuh"
 #include "mlp_pre.cuh"
 #include "chain_kernels.cuh"
 #include "optim_kernels.cuh"
@@ -48,6 +49,8 @@ struct bt_ctx {
     Tc3Net tc3{};                       // pair kernel, third generation (mlp_tc3.cuh)
     Tc3Net tc3p{};                      // same, starting after the leading small blocks (evaluated by mlp_pre.cuh)
     PreNet preb{};                      // warp-level tensor-core pre-pass (weights of the leading blocks)
+    Tc4Net tc4{};                       // column-major pair kernel (mlp_tc4.cuh), the default
+    PreNet preb4{};                     // its pre-pass (same kernel, constant-one bias features in the image)
     uint8_t* pre_img = nullptr;         // activation image of K-blocks [0, pre_kb) written by the pre-pass
     size_t pre_cap = 0;
     Tc2Net tc2{};                       // same for the cta_group::2 kernel (mlp_tc2.cuh)
@@ -163,6 +166,8 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
     tc3_free(c->tc3);
     tc3_free(c->tc3p);
     preb_free(c->preb);
+    tc4_free(c->tc4);
+    preb_free(c->preb4);
     if (c->pre_img) cudaFree(c->pre_img);
     void* ptrs[] = {c->obs, c->nbr, c->gid, c->site_pix, c->theta, c->v, c->nll_lik, c->grad_lik, c->lf_cache, c->jt,
                     c->accept, c->logpa, c->accepted_any, c->rows, c->lf_rows, c->jac_rows, c->nl, c->logq, c->objc,
@@ -185,13 +190,15 @@ extern "C" int bt_set_mlp_mode(bt_ctx* c, int mode) {
 }
 extern "C" int bt_synchronize(bt_ctx* c) { REQUIRE(c, "null ctx"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return 0; }
 extern "C" int64_t bt_kernel_launches(bt_ctx* c) { return c ? c->launches : -1; }
-// which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 4 = pair kernel fed by the pre-pass
+// which tensor-core forward-map kernel BT_MLP_BF16_TC runs for the uploaded network: 5 = column-major pair kernel fed by the
+// pre-pass (mlp_pre.cuh + mlp_tc4.cuh, default), 4 = previous pair kernel fed by the pre-pass
 // (mlp_pre.cuh + mlp_tc3.cuh, default), 3 = pair kernel alone (mlp_tc3.cuh),
 // 1 = single-CTA kernel (mlp_tc.cuh; also the fallback for shapes the pair kernel does not take), 2 = first cta_group::2 kernel
 static int tc_variant(const bt_ctx* c) {
-    static const int want = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 4;
-    if (want == 4 && c->tc3p.ready && c->preb.ready) return 4;
-    if ((want == 3 || want == 4) && c->tc3.ready) return 3;
+    static const int want = getenv("BT_TC_VARIANT") ? atoi(getenv("BT_TC_VARIANT")) : 5;
+    if (want == 5 && c->tc4.ready && c->preb4.ready) return 5;
+    if ((want == 4 || want == 5) && c->tc3p.ready && c->preb.ready) return 4;
+    if ((want == 3 || want == 4 || want == 5) && c->tc3.ready) return 3;
     if (want == 2 && c->tc2.ready) return 2;
     return c->tc.ready ? 1 : 0;
 }
@@ -270,6 +277,15 @@ extern "C" int bt_upload_network(bt_ctx* c, int n_in, int order, int n_feat0, co
         if (c->tc3p.ready && !(c->tc3p.sched.U[c->tc3p.sched.n_units - 1].flags & TC3_F_CONT)) tc3_free(c->tc3p);
         preb_free(c->preb);
         if (c->tc3p.ready) preb_build(c->preb, n_feat0, skip, block_new, weights, biases);
+    }
+    {   // column-major pair kernel + its pre-pass (the default whenever the shapes fit)
+        tc4_free(c->tc4);
+        preb_free(c->preb4);
+        if (tc4_build(c->tc4, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, LOGE10) < 0) return fail("tc4_build", __FILE__, __LINE__);
+        if (c->tc4.ready) {
+            if (preb_build(c->preb4, n_feat0, c->tc4.n_pre, block_new, weights, biases, c->tc4.sched.one_pos) < 0) return fail("preb_build", __FILE__, __LINE__);
+            if (!c->preb4.ready || c->preb4.dev.pre_kb != c->tc4.sched.pre_kb) { tc4_free(c->tc4); preb_free(c->preb4); }
+        }
     }
     return 0;
 }
@@ -444,22 +460,26 @@ static int run_mlp(bt_ctx* c, const float* rows, int M, float* lf, float* jac) {
         // the emulator must be ONE deterministic function of theta whichever launch evaluates it -- MTM compares candidates
         // (forward-only launch) with the cached value of the current state (evaluated with its Jacobian)
         const int variant = tc_variant(c);
-        if (variant == 4) {
-            const size_t need = pre_image_bytes(M, jac ? 1 + c->fm.T : 1, c->tc3p.sched.pre_kb);
+        if (variant == 4 || variant == 5) {
+            const size_t need = pre_image_bytes(M, jac ? 1 + c->fm.T : 1, variant == 5 ? c->tc4.sched.pre_kb : c->tc3p.sched.pre_kb);
             if (need > c->pre_cap) {
                 if (c->pre_img) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->pre_img); c->pre_img = nullptr; c->pre_cap = 0; }
                 CK(cudaMalloc(&c->pre_img, need + need / 8));
                 c->pre_cap = need + need / 8;
             }
             c->tc3p.sched.pre_img = c->pre_img;
+            c->tc4.sched.pre_img = c->pre_img;
             static const bool pre_simt = getenv("BT_PRE_SIMT") != nullptr;     // CUDA-core reference version of the pre-pass
-            const int prc = (c->preb.ready && !pre_simt)
+            const int prc = variant == 5
+                ? preb_launch(c->preb4, c->fm, c->net, rows, M, jac != nullptr, c->pre_img, c->sm_count, c->stream)
+                : (c->preb.ready && !pre_simt)
                 ? preb_launch(c->preb, c->fm, c->net, rows, M, jac != nullptr, c->pre_img, c->sm_count, c->stream)
                 : pre_launch(c->tc3p, c->fm, c->net, rows, M, jac != nullptr, c->pre_img, c->sm_count, c->stream);
             if (prc) return fail("pre-pass launch failed", __FILE__, __LINE__);
             KLAUNCH(c);
         }
-        int rc = variant == 4 ? tc3_launch(c->tc3p, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
+        int rc = variant == 5 ? tc4_launch(c->tc4, c->fm, rows, M, lf, jac, c->sm_count, c->stream)
+               : variant == 4 ? tc3_launch(c->tc3p, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
                : variant == 3 ? tc3_launch(c->tc3, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
                : variant == 2 ? tc2_launch(c->tc2, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream)
                               : tc_launch(c->tc, c->fm, c->net, rows, M, lf, jac, c->sm_count, c->stream);

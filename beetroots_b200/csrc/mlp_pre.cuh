@@ -144,6 +144,7 @@ struct PreNetDev {
     int n_pre, F0, pre_kb;
     int in_[PREB_MAX], new_[PREB_MAX], npad[PREB_MAX], kpad[PREB_MAX], woff[PREB_MAX], wpitch[PREB_MAX], boff[PREB_MAX];
     int wbytes, nbias;
+    int one_pos;                       // >= 0: features one_pos, one_pos + 1 of a primal column are the constant 1 (bias inputs of mlp_tc4.cuh)
     const uint8_t* wimg;               // per block [npad][wpitch] bf16, K-major, rows >= new and k >= in zero
     const float* bias;                 // per block [npad], zero padded
 };
@@ -158,12 +159,12 @@ static inline void preb_free(PreNet& p) {
     p = PreNet();
 }
 static inline int preb_build(PreNet& p, int n_feat0, int n_pre, const int32_t* block_new, const double* const* weights,
-                             const double* const* biases) {
+                             const double* const* biases, int one_pos = -1) {
     p.ready = false;
     if (n_pre < 1 || n_pre > PREB_MAX || n_feat0 > 64) return 0;
     PreNetDev& d = p.dev;
     memset(&d, 0, sizeof d);
-    d.n_pre = n_pre; d.F0 = n_feat0;
+    d.n_pre = n_pre; d.F0 = n_feat0; d.one_pos = one_pos;
     int in = n_feat0, wb = 0, nb = 0;
     for (int l = 0; l < n_pre; ++l) {
         d.in_[l] = in;
@@ -177,8 +178,8 @@ static inline int preb_build(PreNet& p, int n_feat0, int n_pre, const int32_t* b
         nb += d.npad[l];
         in += block_new[l];
     }
-    if (in > 192) return 0;
-    d.pre_kb = (in + TC_BK - 1) / TC_BK;
+    if (in > 192 || (one_pos >= 0 && (one_pos < in || one_pos + 2 > 192))) return 0;
+    d.pre_kb = ((one_pos >= 0 ? one_pos + 2 : in) + TC_BK - 1) / TC_BK;
     d.wbytes = wb; d.nbias = nb;
     std::vector<uint8_t> w(wb, 0);
     std::vector<float> b(nb, 0.f);
@@ -318,6 +319,13 @@ mlp_pre_mma_kernel(PreNetDev pn, NetDev net, FmapDev fm, const float* __restrict
                         }
                     }
             }
+            __syncwarp();
+        }
+        if (pn.one_pos >= 0) {     // constant-one features of the primal columns (after the blocks: their padded rows wrote zeros here)
+            const long long gc = (long long)grp * 32 + lane;
+            const int row = (int)(gc / S), s = (int)(gc - (long long)row * S);
+            uint16_t* hrow = reinterpret_cast<uint16_t*>(Hw + (size_t)lane * PREB_PITCH);
+            hrow[pn.one_pos] = hrow[pn.one_pos + 1] = (s == 0 && row < M) ? (uint16_t)0x3F80 : (uint16_t)0;
             __syncwarp();
         }
         // ---- image of my 32 columns: pair-tile / CTA half / rows of the SWIZZLE_128B K-block tiles

@@ -1,0 +1,814 @@
+// Forward map kernel, tcgen05 cta_group::2, fourth generation ("column-major pair kernel", the default bf16 path).
+//
+// Orientation: the COLUMNS of a tile are the M dimension of the MMA,
+//     D[128 columns, n out features] += H[128 columns, k] (A, K-major) x W[n, k] (B, K-major)     UMMA M = 128, N = n, K = 16
+// cta_group::2: CTA c holds its 64 columns of H (its resident activation buffer, 64 rows x 64 features x bf16 per
+// K-block, SWIZZLE_128B) and half of the n weight rows of a chunk; its TMEM receives D for its 64 columns: lanes
+// [0, 64) hold features [0, n/2) of the chunk, lanes [64, 128) features [n/2, n), column = feature mod n/2 (measured,
+// scripts/umma3_bench.cu part B).  Measured rate (part A): n/4 cycles per MMA for n >= 128 = the dense bf16 peak, 29
+// cycles for n = 96, 25 for n <= 64 -- so the live rows of a block are padded to a multiple of 16 only (the previous
+// orientation, features as M = 256, paid 16.5 k MMA cycles per tile for 10.7 k useful ones).
+// What the orientation buys besides:
+//   * a thread of the activation epilogue owns ONE column and 8 consecutive features: one tcgen05.ld, 8 x (2 GELU),
+//     four cvt.rn.bf16x2 and ONE conflict-free 16-byte st.shared into the CTA's OWN activation buffer -- no 2-byte
+//     transposing stores, no st.shared::cluster, no row replication for small blocks;
+//   * biases ride in the GEMM: two constant-one features (positions one_pos, one_pos + 1 of the input K-blocks, written
+//     by the pre-pass for primal columns, zero for tangent columns) meet weight columns bf16(b) and bf16(b - bf16(b));
+//   * a block is cut into chunks of <= nc_max features with their own accumulators; chunk c's epilogue runs under
+//     chunk c+1's MMAs, and the first chunk of the next block starts on the K-blocks that are already complete;
+//   * the output layer rides as 16 (32) extra rows of the last chunk of the last hidden block over the K range they
+//     share and is finished by a short continuation (N = 16 MMAs onto the same TMEM columns);
+//   * the next tile's input K-blocks (pre-pass image, mlp_pre.cuh) are brought in by ONE bulk copy as soon as the last
+//     MMA reading them has completed.
+// The schedule is a flat list of steps (one weight chunk x one K-block = up to 4 MMAs) and a list of chunks built on
+// the host (tc4_build); every pipeline role walks the same lists.  Roles per CTA: warps 20-23 weight producers (one
+// bulk copy in flight each; copies of one warp complete serially, scripts/tma_bench.cu), warp 24 MMA issuer (leader),
+// warps 18-19 "chunk landed" relays (peer), warp 16 input loader, warp 17 "chunk drained" forwarder (peer), warps 0-15 epilogue.
+#pragma once
+#include "mlp_pre.cuh"
+
+// Warp roles.  The warp scheduler of an SM sub-partition prefers the HIGHEST warp id among its eligible warps (measured on
+// Blackwell, B300_MICROARCH.md "multi-warp arbiter"), and a warp's sub-partition is its id mod 4: the MMA issuer is the
+// highest warp of the CTA so that the 16 epilogue warps (4 per sub-partition, math heavy) cannot starve it -- with the
+// issuer at warp 4 its steps stalled for 700+ cycles whenever an epilogue was running.
+#define TC4_THREADS 800
+#define TC4_EW0 0                  // first epilogue warp (its TMEM lane quarter = warp id mod 4)
+#define TC4_W_LOADER 16
+#define TC4_W_FWD 17
+#define TC4_W_RELAY0 18
+#define TC4_W_RELAY1 19
+#define TC4_W_PROD0 20
+#define TC4_W_ISSUER 24
+#define TC4_NEW 16                 // epilogue warps
+#define TC4_NPROD 4
+#define TC4_MAX_STEPS 176
+#define TC4_MAX_CHUNKS 16
+#define TC4_MAX_SLOTS 8
+#define TC4_MISC_BYTES 1024
+#define TC4_MAX_SEGS 64
+#define TC4_F_ACC0 1               // first MMA of the step overwrites the accumulator
+#define TC4_F_WAIT_IN 2            // wait for the tile's input K-blocks
+#define TC4_F_KBFREE 4             // after this step nothing of this tile reads the input K-blocks any more
+#define TC4_F_OFF 8                // the step belongs to the NEXT tile of the iteration (cross-tile software pipeline)
+
+struct Tc4Step {                   // 16 bytes
+    uint32_t w_off;                // 128-byte rows into the CTA's weight stream
+    uint16_t rows;                 // weight rows per CTA (= N / 2)
+    uint16_t tcol;                 // TMEM column of the accumulator
+    uint8_t kb, ks_lo, ks_hi, flags;
+    int8_t wait[2];                // "chunk drained" barriers of this tile to wait for (-1: none)
+    int8_t wait_prev;              // same, of the previous tile
+    int8_t commit;                 // "accumulator complete" barrier to commit after this step (-1: none)
+};
+// A segment = consecutive steps of one chunk without a wait or a signal in between: what the device roles iterate over
+// (the per-step work of the MMA issuer must be a handful of instructions: 4 MMAs of N = 144 take 144 cycles).
+struct Tc4Seg {                    // 20 bytes
+    uint32_t w_off;                // 128-byte rows into the CTA's weight stream, first step
+    uint16_t rows, tcol;
+    uint8_t kb0, kb1;              // K-blocks [kb0, kb1)
+    uint8_t ks_lo, ks_hi;          // 16-feature steps [ks_lo, 4) of kb0 ... [0, ks_hi) of kb1 - 1
+    int8_t wait[2], wait_prev, commit;
+    uint8_t flags, pad[3];
+};
+static_assert(sizeof(Tc4Seg) == 20, "Tc4Seg layout");
+struct Tc4Chunk {                  // 12 bytes, the epilogue's view
+    uint16_t tcol;
+    uint16_t pos[2];               // activation position of the first feature of each lane half
+    uint8_t units[2];              // live 8-feature units per lane half
+    uint8_t kind;                  // 0: activation, 1: network outputs
+    uint8_t off;                   // 1: belongs to the next tile of the iteration
+    uint8_t pad[2];
+};
+struct Tc4Sched {
+    int n_steps, n_segs, n_chunks, n_slots, slot_bytes, act_kb, n_out, out_pad, pre_kb, one_pos;
+    // the lists live in the kernel's parameter (constant) bank: the MMA issuer's loop then runs on the uniform datapath
+    // (values loaded from shared memory count as divergent and every tcgen05 operand costs a vector->uniform move)
+    Tc4Seg segs[TC4_MAX_SEGS];
+    Tc4Chunk chunks[TC4_MAX_CHUNKS];
+    const uint8_t* wstream[2];
+    const uint8_t* pre_img;
+    long long* dbg;
+    int dbg_flags;                 // DBG instantiation only (results invalid): 1 no weight copies, 2 relay does not wait, 4 no MMAs, 8 no activation math
+};
+struct Tc4Net {
+    bool ready = false;
+    Tc4Sched sched{};
+    void* d_w[2] = {nullptr, nullptr};
+    size_t smem_bytes = 0;
+    int n_pre = 0;
+    double mma_cycles = 0;         // model: sum over MMAs of the measured cycles per instruction
+    std::vector<Tc4Step> h_steps;
+    std::vector<Tc4Seg> h_segs;
+    std::vector<Tc4Chunk> h_chunks;
+    std::vector<uint16_t> h_w[2];  // kept only when built without upload (host-side checks, tests/tc4_sched_check.cu)
+};
+static inline void tc4_free(Tc4Net& t) {
+    for (int c = 0; c < 2; ++c) if (t.d_w[c]) cudaFree(t.d_w[c]);
+    t = Tc4Net();
+}
+static inline int tc4_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Leading blocks the pre-pass can take: their concatenated features + 2 constants must fit 3 K-blocks, at most
+// PREB_MAX blocks, and at least one hidden block must remain for this kernel.
+static inline int tc4_choose_pre(int n_feat0, int n_blocks, const int32_t* block_new) {
+    int in = n_feat0, n = 0;
+    for (int l = 0; l < n_blocks - 1 && l < PREB_MAX; ++l) {
+        const int npad = tc4_round_up(block_new[l], 16);
+        if (in + npad > 192 || in + block_new[l] + 2 > 192) break;
+        in += block_new[l];
+        n = l + 1;
+    }
+    return n;
+}
+
+// Host-side schedule + weight streams.  Returns 0 (t.ready tells whether the shapes fit) or -1 on a CUDA error.
+// mode: 0 = steps in natural order; 1 = first block of the next tile issued before the output continuation of this one.
+static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int32_t* block_new, const double* const* weights,
+                                 const double* const* biases, const double* w_out, int n_out, double out_scale, int nc_max,
+                                 int mode, bool upload) {
+    t.ready = false;
+    if (nc_max < 64 || nc_max > 256 || nc_max % 16) return 0;
+    if (n_blocks < 2 || n_blocks > BT_MAX_BLOCKS || n_out < 1 || n_out > 32 || n_feat0 > 64) return 0;
+    const int n_pre = tc4_choose_pre(n_feat0, n_blocks, block_new);
+    if (n_pre < 1) return 0;
+    Tc4Sched& s = t.sched;
+    memset(&s, 0, sizeof s);
+    t.n_pre = n_pre;
+    const int out_pad = tc4_round_up(n_out, 16);
+    // ---- positions in the activation buffer
+    std::vector<int> in_orig(n_blocks + 1), lpos(n_blocks, -1);
+    in_orig[0] = n_feat0;
+    for (int l = 0; l < n_blocks; ++l) in_orig[l + 1] = in_orig[l] + block_new[l];
+    const int n_feat = in_orig[n_blocks];
+    const int pre_feats = in_orig[n_pre], one_pos = pre_feats;
+    s.one_pos = one_pos;
+    s.pre_kb = (pre_feats + 2 + TC_BK - 1) / TC_BK;
+    if (s.pre_kb > 3) return 0;
+    int pos = tc4_round_up(pre_feats + 2, 16);
+    for (int l = n_pre; l < n_blocks; ++l) { lpos[l] = pos; pos = tc4_round_up(pos + block_new[l], 16); }
+    const int n_pos = pos;
+    s.act_kb = (n_pos + TC_BK - 1) / TC_BK;
+    s.n_out = n_out;
+    s.out_pad = out_pad;
+    // position -> original feature (-1: padding, -2 / -3: constant one, high / low part of the bias)
+    std::vector<int> orig(s.act_kb * TC_BK, -1);
+    for (int k = 0; k < pre_feats; ++k) orig[k] = k;
+    orig[one_pos] = -2; orig[one_pos + 1] = -3;
+    for (int l = n_pre; l < n_blocks; ++l) for (int f = 0; f < block_new[l]; ++f) orig[lpos[l] + f] = in_orig[l] + f;
+    // ---- chunks
+    struct RowSrc { int layer, row; };          // layer -1: output layer, -2: padding
+    struct HChunk { int layer, n, cols, tcol, gelu_n, klo_pos, khi_pos; std::vector<RowSrc> rows[2]; };
+    std::vector<HChunk> chunks;
+    std::vector<int> first_chunk(n_blocks + 1, 0);
+    for (int l = n_pre; l < n_blocks; ++l) {
+        first_chunk[l] = (int)chunks.size();
+        const bool last = l == n_blocks - 1;
+        const int npad = tc4_round_up(block_new[l], 16) + (last ? out_pad : 0);
+        const int units = npad / 16, nch = (npad + nc_max - 1) / nc_max;
+        int cbase = 0;
+        for (int c = 0; c < nch; ++c) {
+            // (the chunk carrying the output rows is the last one and the largest)
+            const int rc = nch - 1 - c;
+            const int n = 16 * (units / nch + (rc < units % nch ? 1 : 0));
+            const bool with_out = last && c == nch - 1;
+            const int G = n - (with_out ? out_pad : 0);
+            if (G < 0 || (with_out && G < 16)) return 0;
+            HChunk h;
+            h.layer = l; h.n = n; h.cols = n / 2; h.tcol = 0; h.gelu_n = G; h.klo_pos = 0; h.khi_pos = lpos[l];
+            for (int hh = 0; hh < 2; ++hh) {
+                h.rows[hh].assign(n / 2, RowSrc{-2, 0});
+                for (int j = 0; j < G / 2; ++j) {
+                    const int f = cbase + hh * (G / 2) + j;
+                    if (f < block_new[l]) h.rows[hh][j] = RowSrc{l, f};
+                }
+                if (with_out)
+                    for (int j = 0; j < out_pad / 2; ++j) {
+                        const int o = hh * (out_pad / 2) + j;
+                        if (o < n_out) h.rows[hh][G / 2 + j] = RowSrc{-1, o};
+                    }
+            }
+            chunks.push_back(h);
+            cbase += G;
+        }
+    }
+    first_chunk[n_blocks] = (int)chunks.size();
+    const int n_gelu_chunks = (int)chunks.size();
+    {   // output continuation: N = out_pad onto the columns of the output rows of the last chunk
+        HChunk h;
+        h.layer = -1; h.n = out_pad; h.cols = out_pad / 2; h.tcol = 0; h.gelu_n = 0;
+        h.klo_pos = lpos[n_blocks - 1]; h.khi_pos = n_pos;
+        for (int hh = 0; hh < 2; ++hh) {
+            h.rows[hh].assign(out_pad / 2, RowSrc{-2, 0});
+            for (int j = 0; j < out_pad / 2; ++j) if (hh * (out_pad / 2) + j < n_out) h.rows[hh][j] = RowSrc{-1, hh * (out_pad / 2) + j};
+        }
+        chunks.push_back(h);
+    }
+    const int n_chunks = (int)chunks.size();
+    if (n_chunks > TC4_MAX_CHUNKS) return 0;
+    // ---- TMEM: blocks alternate between two regions, the chunk with the output rows has its own
+    {
+        int width[2] = {0, 0};
+        for (int l = n_pre; l < n_blocks; ++l) {
+            int w = 0;
+            for (int c = first_chunk[l]; c < first_chunk[l + 1]; ++c) if (c != n_gelu_chunks - 1) w += chunks[c].cols;
+            width[(l - n_pre) & 1] = std::max(width[(l - n_pre) & 1], w);
+        }
+        const int r2 = width[0] + width[1];
+        if (r2 + chunks[n_gelu_chunks - 1].cols > 512) return 0;
+        for (int l = n_pre; l < n_blocks; ++l) {
+            int col = ((l - n_pre) & 1) ? width[0] : 0;
+            for (int c = first_chunk[l]; c < first_chunk[l + 1]; ++c) {
+                if (c == n_gelu_chunks - 1) chunks[c].tcol = r2;
+                else { chunks[c].tcol = col; col += chunks[c].cols; }
+            }
+        }
+        chunks[n_chunks - 1].tcol = r2 + chunks[n_gelu_chunks - 1].gelu_n / 2;
+    }
+    // ---- issue order of the chunks within one iteration (mode 1: first block of the next tile before the continuation)
+    struct Item { int chunk, off; };
+    std::vector<Item> order;
+    const int fb_end = first_chunk[n_pre + 1];           // chunks of the first block: [0, fb_end)
+    if (mode == 1 && fb_end < n_gelu_chunks) {
+        for (int c = fb_end; c < n_gelu_chunks; ++c) order.push_back({c, 0});
+        for (int c = 0; c < fb_end; ++c) order.push_back({c, 1});
+        order.push_back({n_chunks - 1, 0});
+    } else {
+        mode = 0;
+        for (int c = 0; c < n_chunks; ++c) order.push_back({c, 0});
+    }
+    // ---- steps, with the waits each one needs
+    // Chunk c is "drained" (barrier done[c]) when every epilogue warp has read its accumulators and written + fenced its
+    // features.  A step waits (a) for the chunks that wrote the features of its K-block, (b) before overwriting TMEM
+    // columns, for the chunks that last lived there.  The issuer's waits are cumulative, so a wait already implied by an
+    // earlier step of the same list position is dropped.  The simulation runs three iterations to reach the steady state.
+    std::vector<Tc4Step> steps;
+    std::vector<std::vector<RowSrc>> step_rows[2];
+    std::vector<int> step_chunk, step_kb;
+    {
+        // owner of every TMEM column and of every activation position: (chunk, tile) of the last writer
+        struct Own { int chunk, tile; };
+        std::vector<Own> tm(512, Own{-1, -1});
+        // highest tile whose done[c] the issuer has waited for, by steps of the tile's own iteration (0) and by steps that run
+        // one iteration early (1).  The latter are skipped in the last iteration, so own-iteration steps must not rely on them.
+        std::vector<int> waited_tile[2] = {std::vector<int>(n_chunks, -1000), std::vector<int>(n_chunks, -1000)};
+        for (int it = -1; it < 3; ++it) {
+            const bool emit = it == 2;
+            for (const Item& im : order) {
+                const int tile = it + im.off;
+                if (tile < 0) continue;
+                const HChunk& h = chunks[im.chunk];
+                const bool is_cont = h.layer == -1;
+                const int kb0 = h.klo_pos / TC_BK, kb1 = (h.khi_pos + TC_BK - 1) / TC_BK;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    Tc4Step st;
+                    memset(&st, 0, sizeof st);
+                    st.rows = (uint16_t)(h.n / 2);
+                    st.tcol = (uint16_t)h.tcol;
+                    st.kb = (uint8_t)kb;
+                    st.ks_lo = (uint8_t)(kb == kb0 ? (h.klo_pos % TC_BK) / 16 : 0);
+                    st.ks_hi = (uint8_t)(kb == kb1 - 1 ? (h.khi_pos - kb * TC_BK + 15) / 16 : 4);
+                    st.flags = (uint8_t)((im.off ? TC4_F_OFF : 0) | ((kb == kb0 && !is_cont) ? TC4_F_ACC0 : 0));
+                    st.wait[0] = st.wait[1] = st.wait_prev = st.commit = -1;
+                    std::vector<std::pair<int, int>> need;    // (chunk, tile)
+                    // (a) features of this K-block: written by chunks of THIS tile (positions < khi_pos only)
+                    for (int c = 0; c < n_gelu_chunks; ++c) {
+                        const HChunk& w = chunks[c];
+                        for (int hh = 0; hh < 2; ++hh) {
+                            int cb = 0;
+                            for (int cc = first_chunk[w.layer]; cc < c; ++cc) cb += chunks[cc].gelu_n;
+                            const int p0 = lpos[w.layer] + cb + hh * (w.gelu_n / 2), p1 = p0 + w.gelu_n / 2;
+                            const int lo = std::max(p0, std::max(kb * TC_BK, h.klo_pos)), hi = std::min(p1, std::min((kb + 1) * TC_BK, h.khi_pos));
+                            if (lo < hi) need.push_back({c, tile});
+                        }
+                    }
+                    // (b) TMEM columns about to be overwritten
+                    if (st.flags & TC4_F_ACC0)
+                        for (int q = h.tcol; q < h.tcol + h.cols; ++q)
+                            if (tm[q].chunk >= 0) need.push_back({tm[q].chunk, tm[q].tile});
+                    // the continuation accumulates onto columns owned by the last activation chunk of its own tile: no hazard
+                    int nw = 0;
+                    for (auto& nd : need) {
+                        if (waited_tile[0][nd.first] >= nd.second || (im.off && waited_tile[1][nd.first] >= nd.second)) continue;
+                        waited_tile[im.off][nd.first] = nd.second;
+                        if (nd.second == tile) { if (nw >= 2) return 0; st.wait[nw++] = (int8_t)nd.first; }
+                        else if (nd.second == tile - 1) { if (st.wait_prev >= 0) return 0; st.wait_prev = (int8_t)nd.first; }
+                        else return 0;
+                    }
+                    if (kb == kb1 - 1) st.commit = (int8_t)im.chunk;
+                    if (emit) { steps.push_back(st); step_chunk.push_back(im.chunk); step_kb.push_back(kb); }
+                }
+                if (!is_cont) for (int q = h.tcol; q < h.tcol + h.cols; ++q) tm[q] = Own{im.chunk, tile};
+                else for (int q = h.tcol; q < h.tcol + h.cols; ++q) tm[q] = Own{im.chunk, tile};
+            }
+        }
+    }
+    // the tile's inputs: the first step of a tile that reads an input K-block waits for them; the last one releases them
+    {
+        // in tile order: off = 1 items come first in the life of a tile (they run in the previous iteration)
+        int first = -1, last = -1;
+        for (int pass = 1; pass >= 0; --pass)
+            for (int i = 0; i < (int)steps.size(); ++i)
+                if (((steps[i].flags & TC4_F_OFF) ? 1 : 0) == pass && steps[i].kb < s.pre_kb) { if (first < 0) first = i; last = i; }
+        for (auto& st : steps) st.flags &= ~(TC4_F_WAIT_IN | TC4_F_KBFREE);
+        if (first < 0) return 0;
+        steps[first].flags |= TC4_F_WAIT_IN;
+        steps[last].flags |= TC4_F_KBFREE;
+        if (steps[last].flags & TC4_F_OFF) return 0;              // inputs must be released within the tile's own iteration
+    }
+    const int n_steps = (int)steps.size();
+    if (n_steps > TC4_MAX_STEPS) return 0;
+    // ---- ring
+    int max_rows = 0;
+    for (auto& st : steps) max_rows = std::max<int>(max_rows, st.rows);
+    s.slot_bytes = tc4_round_up(max_rows * 128, 1024);
+    const long ring = 227L * 1024 - 1024 - (long)s.act_kb * TC_KB_BYTES - TC4_MISC_BYTES;
+    s.n_slots = (int)std::min<long>(TC4_MAX_SLOTS, ring / s.slot_bytes);
+    if (getenv("BT_TC4_SLOTS")) s.n_slots = std::min(s.n_slots, atoi(getenv("BT_TC4_SLOTS")));
+    // A producer waits for "slot free" by phase parity, which tells two consecutive uses of a slot apart but not three: the
+    // producer of step g last synchronised on the consumption of step g - NPROD - n_slots and must be sure that step
+    // g - 2 n_slots has been consumed, hence n_slots >= NPROD.
+    if (s.n_slots < TC4_NPROD) return 0;
+    t.smem_bytes = 1024 + (size_t)s.act_kb * TC_KB_BYTES + (size_t)s.n_slots * s.slot_bytes + TC4_MISC_BYTES;
+    // ---- weight streams (one per CTA, in step order; every step = rows x 64 k, the SW128 shared-memory image)
+    {
+        uint32_t off = 0;
+        for (auto& st : steps) { st.w_off = off; off += st.rows; }
+        for (int c = 0; c < 2; ++c) {
+            std::vector<uint16_t> ws((size_t)off * 64 + 64, 0);
+            for (int i = 0; i < n_steps; ++i) {
+                const HChunk& h = chunks[step_chunk[i]];
+                uint16_t* dst = ws.data() + (size_t)steps[i].w_off * 64;
+                const int kb = step_kb[i];
+                for (int r = 0; r < h.n / 2; ++r) {
+                    const RowSrc rs = h.rows[c][r];
+                    if (rs.layer == -2) continue;
+                    const bool is_out = rs.layer == -1;
+                    const int ld = is_out ? n_feat : in_orig[rs.layer];
+                    const double* W = is_out ? w_out : weights[rs.layer];
+                    for (int kk = 0; kk < TC_BK; ++kk) {
+                        const int p = kb * TC_BK + kk;
+                        if (p < h.klo_pos || p >= h.khi_pos) continue;
+                        const int o = orig[p];
+                        double v;
+                        if (o == -1) continue;
+                        if (o <= -2) {
+                            if (is_out) continue;                         // the output bias lives on the host (shift of ln f)
+                            const float b = (float)biases[rs.layer][rs.row];
+                            const uint16_t hi = f32_to_bf16_rne(b);
+                            uint32_t hb = (uint32_t)hi << 16; float hf; memcpy(&hf, &hb, 4);
+                            dst[sw128_offset((uint32_t)r, (uint32_t)kk) / 2] = o == -2 ? hi : f32_to_bf16_rne(b - hf);
+                            continue;
+                        }
+                        if (o >= ld) continue;
+                        // activations at positions >= n_feat0 are stored as 2 x GELU: halve those weights (exact)
+                        v = (o >= n_feat0 ? 0.5 : 1.0) * (is_out ? out_scale : 1.0) * W[(size_t)rs.row * ld + o];
+                        dst[sw128_offset((uint32_t)r, (uint32_t)kk) / 2] = f32_to_bf16_rne((float)v);
+                    }
+                }
+            }
+            if (!upload) t.h_w[c] = ws;
+            if (upload) {
+                if (cudaMalloc(&t.d_w[c], ws.size() * 2) != cudaSuccess) return -1;
+                if (cudaMemcpy(t.d_w[c], ws.data(), ws.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+                s.wstream[c] = (const uint8_t*)t.d_w[c];
+            }
+        }
+    }
+    // ---- the epilogue's chunk list, in issue order
+    std::vector<Tc4Chunk> ech;
+    std::vector<int> order_pos(n_chunks, -1);
+    for (int i = 0; i < (int)order.size(); ++i) order_pos[order[i].chunk] = i;
+    for (const Item& im : order) {
+        const HChunk& h = chunks[im.chunk];
+        Tc4Chunk e;
+        memset(&e, 0, sizeof e);
+        e.tcol = (uint16_t)h.tcol;
+        e.off = (uint8_t)im.off;
+        if (h.layer == -1) {
+            e.kind = 1;
+            e.units[0] = e.units[1] = (uint8_t)(out_pad / 16);
+        } else {
+            int cb = 0;
+            for (int cc = first_chunk[h.layer]; cc < im.chunk; ++cc) cb += chunks[cc].gelu_n;
+            for (int hh = 0; hh < 2; ++hh) {
+                const int f0 = cb + hh * (h.gelu_n / 2);
+                e.pos[hh] = (uint16_t)(lpos[h.layer] + f0);
+                const int live = std::max(0, std::min(block_new[h.layer] - f0, h.gelu_n / 2));
+                e.units[hh] = (uint8_t)((live + 7) / 8);
+            }
+        }
+        ech.push_back(e);
+    }
+    // barrier ids in the steps refer to positions in the issue-ordered chunk list
+    for (auto& st : steps) {
+        for (int k = 0; k < 2; ++k) if (st.wait[k] >= 0) st.wait[k] = (int8_t)order_pos[st.wait[k]];
+        if (st.wait_prev >= 0) st.wait_prev = (int8_t)order_pos[st.wait_prev];
+        if (st.commit >= 0) st.commit = (int8_t)order_pos[st.commit];
+    }
+    s.n_steps = n_steps;
+    s.n_chunks = n_chunks;
+    // ---- segments
+    std::vector<Tc4Seg> segs;
+    for (int i = 0; i < n_steps; ++i) {
+        const Tc4Step& st = steps[i];
+        bool fresh = segs.empty();
+        if (!fresh) {
+            const Tc4Step& pv = steps[i - 1];
+            fresh = step_chunk[i] != step_chunk[i - 1] || st.kb != pv.kb + 1 || st.wait[0] >= 0 || st.wait[1] >= 0 || st.wait_prev >= 0 ||
+                    (st.flags & (TC4_F_WAIT_IN | TC4_F_ACC0)) || pv.commit >= 0 || (pv.flags & TC4_F_KBFREE) || pv.ks_hi != 4 || st.ks_lo != 0 ||
+                    ((st.flags ^ pv.flags) & TC4_F_OFF);
+        }
+        if (fresh) {
+            Tc4Seg g;
+            memset(&g, 0, sizeof g);
+            g.w_off = st.w_off; g.rows = st.rows; g.tcol = st.tcol; g.kb0 = st.kb; g.kb1 = (uint8_t)(st.kb + 1);
+            g.ks_lo = st.ks_lo; g.ks_hi = st.ks_hi;
+            g.wait[0] = st.wait[0]; g.wait[1] = st.wait[1]; g.wait_prev = st.wait_prev; g.commit = st.commit;
+            g.flags = st.flags;
+            segs.push_back(g);
+        } else {
+            Tc4Seg& g = segs.back();
+            g.kb1 = (uint8_t)(st.kb + 1);
+            g.ks_hi = st.ks_hi;
+            g.commit = st.commit;
+            g.flags |= st.flags & TC4_F_KBFREE;
+        }
+    }
+    s.n_segs = (int)segs.size();
+    t.h_segs = segs;
+    if (segs.size() > TC4_MAX_SEGS) return 0;
+    for (size_t i = 0; i < segs.size(); ++i) s.segs[i] = segs[i];
+    for (size_t i = 0; i < ech.size(); ++i) s.chunks[i] = ech[i];
+    {   // cycle model of the MMA stream (measured cycles per instruction, scripts/umma3_bench.cu)
+        double cyc = 0;
+        for (auto& st : steps) {
+            const int n = 2 * st.rows;
+            cyc += (st.ks_hi - st.ks_lo) * (n >= 128 ? n / 4.0 : (n > 64 ? 25.0 + (n - 64) / 8.0 : 25.0));
+        }
+        t.mma_cycles = cyc;
+    }
+    t.h_steps = steps;
+    t.h_chunks = ech;
+    if (upload) t.ready = true;
+    return 0;
+}
+
+static inline int tc4_build(Tc4Net& t, int n_feat0, int n_blocks, const int32_t* block_new, const double* const* weights,
+                            const double* const* biases, const double* w_out, int n_out, double out_scale, int nc_max = 0,
+                            int mode = -1, bool upload = true) {
+    if (nc_max <= 0) nc_max = getenv("BT_TC4_NCMAX") ? atoi(getenv("BT_TC4_NCMAX")) : 224;
+    if (mode < 0) mode = getenv("BT_TC4_MODE") ? atoi(getenv("BT_TC4_MODE")) : 0;
+    int rc = tc4_build_mode(t, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, out_scale, nc_max, mode, upload);
+    if (rc == 0 && t.h_steps.empty() && mode != 0) {      // the cross-tile order needs more waits per step than a step holds
+        tc4_free(t);
+        rc = tc4_build_mode(t, n_feat0, n_blocks, block_new, weights, biases, w_out, n_out, out_scale, nc_max, 0, upload);
+    }
+    return rc;
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tc4_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t tc4_pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// 2 x GELU of a primal pre-activation / 2 x GELU'(primal) x tangent, the primal living S - 1 lanes below at most
+template <int S>
+__device__ __forceinline__ float tc4_act(float v, int s_col, int src_lane) {
+    if (S == 1) return gelu2_tc(v);
+    const float x = __shfl_sync(0xffffffffu, v, src_lane);        // pre-activation of the primal column
+    const float xc = fminf(fmaxf(x, -8.f), 8.f), x2 = xc * xc;
+    const float t = tanh_mufu(xc * fmaf(x2, fmaf(x2, TC_G2, TC_G1), TC_G0));
+    if (s_col == 0) return fmaf(x, t, x);
+    const float du = fmaf(x2, fmaf(x2, 5.f * TC_G2, 3.f * TC_G1), TC_G0);
+    return ((1.f + t) + xc * (1.f - t * t) * du) * v;
+}
+
+template <int S, int DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC4_THREADS, 1)
+mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __restrict__ rows, int M, float* __restrict__ lf, float* __restrict__ jac) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* act = smem;                                             // [act_kb][64 columns x 64 features bf16, SW128]
+    uint8_t* ring = act + (size_t)sch.act_kb * TC_KB_BYTES;          // [n_slots][slot_bytes]
+    uint8_t* misc = ring + (size_t)sch.n_slots * sch.slot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + 640);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_tfull = smem_u32(bars + 16);
+    const uint32_t bar_done = smem_u32(bars + 32), bar_ldone = smem_u32(bars + 48);
+    const uint32_t bar_infull = smem_u32(bars + 64), bar_inready = smem_u32(bars + 65), bar_kbfree = smem_u32(bars + 66);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    constexpr int P2 = 128 / S;                                      // rows of theta per pair-tile
+    const int n_ptiles = (M + P2 - 1) / P2;
+    const int pt0 = blockIdx.x >> 1, pt_step = gridDim.x >> 1;
+    const int n_my = pt0 < n_ptiles ? (n_ptiles - pt0 + pt_step - 1) / pt_step : 0;
+    const int n_segs = sch.n_segs, n_chunks = sch.n_chunks, n_slots = sch.n_slots;
+    long long* const dbg = DBG == 1 ? sch.dbg : nullptr;
+    constexpr int dflags = DBG >= 2 ? (DBG >> 1) : 0;              // compile-time knock-outs (timing experiments, results invalid)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) { mbar_init(bar_full + 8 * i, (crank == 0 && !(dflags & 16)) ? 2 : 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < 16; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_done + 8 * i, TC4_NEW + 1);                // leader: its 16 epilogue warps + the peer's forwarder
+            mbar_init(bar_ldone + 8 * i, TC4_NEW);                   // peer: its 16 epilogue warps
+        }
+        mbar_init(bar_infull, 1);
+        mbar_init(bar_inready, 2);
+        mbar_init(bar_kbfree, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        uint4* a4 = reinterpret_cast<uint4*>(smem);
+        const int n16 = (sch.act_kb * TC_KB_BYTES + sch.n_slots * sch.slot_bytes) / 16;
+        for (int i = threadIdx.x; i < n16; i += TC4_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    if (warp == TC4_W_ISSUER) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp >= TC4_W_PROD0 && warp < TC4_W_PROD0 + TC4_NPROD) {
+        // ===================== weight producers: step g belongs to producer g mod 4, ring slot g mod n_slots =====================
+        if (lane == 0) {
+            const uint32_t ring_addr = smem_u32(ring);
+            const uint8_t* wsrc = sch.wstream[crank];
+            uint32_t g = 0, slot = 0, use = 0, pstep = 0;
+            for (int it = -1; it < n_my; ++it)
+                for (int si = 0; si < n_segs; ++si) {
+                    const Tc4Seg sg = sch.segs[si];
+                    const int tl = it + ((sg.flags & TC4_F_OFF) ? 1 : 0);
+                    if (tl < 0 || tl >= n_my) continue;
+                    const uint32_t bytes = (uint32_t)sg.rows * 128u;
+                    const uint8_t* src = wsrc + (size_t)sg.w_off * 128;
+                    if (DBG == 1 && si == 0) pstep = 0;
+                    for (int kb = sg.kb0; kb < sg.kb1; ++kb, src += bytes) {
+                        if (DBG == 1) ++pstep;
+                        if ((g & (TC4_NPROD - 1)) == (uint32_t)(warp - TC4_W_PROD0)) {
+                            if (use > 0) mbar_spin(bar_empty + 8 * slot, (use - 1) & 1u);
+                            if (DBG == 1 && dbg && blockIdx.x < 2 && tl == 1 && pstep <= 240) dbg[720 + 240 * blockIdx.x + pstep - 1] = clock64();
+                            if (dflags & 1) mbar_arrive(bar_full + 8 * slot);
+                            else {
+                                mbar_expect_tx(bar_full + 8 * slot, bytes);
+                                bulk_g2s(ring_addr + slot * (uint32_t)sch.slot_bytes, src, bytes, bar_full + 8 * slot);
+                            }
+                        }
+                        ++g;
+                        if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
+                    }
+                }
+        }
+    } else if ((warp == TC4_W_RELAY0 || warp == TC4_W_RELAY1) && crank == 1) {
+        // ===================== relays (peer): "my half of the chunk has landed" -> leader; two threads, alternate steps =====================
+        if (lane == 0) {
+            const uint32_t leader_full = mapa_u32(bar_full, 0);
+            const uint32_t me = warp == TC4_W_RELAY0 ? 0u : 1u;
+            uint32_t g = 0, slot = 0, use = 0;
+            for (int it = -1; it < n_my; ++it)
+                for (int si = 0; si < n_segs; ++si) {
+                    const int tl = it + ((sch.segs[si].flags & TC4_F_OFF) ? 1 : 0);
+                    if (tl < 0 || tl >= n_my) continue;
+                    const int nst = sch.segs[si].kb1 - sch.segs[si].kb0;
+                    for (int k = 0; k < nst; ++k) {
+                        if ((g & 1u) == me) {
+                            if (!(dflags & 2)) mbar_spin(bar_full + 8 * slot, use & 1u);
+                            if (!(dflags & 16)) mbar_arrive_cluster(leader_full + 8 * slot);
+                        }
+                        ++g;
+                        if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
+                    }
+                }
+        }
+    } else if (warp == TC4_W_ISSUER && crank == 0) {
+        // ===================== MMA issuer (leader): the whole warp walks the list, one elected lane issues =====================
+        const bool leader_lane = elect_one();
+        const uint32_t act_addr = smem_u32(act), ring_addr = smem_u32(ring);
+        const uint32_t desc_lo0 = 1u << 16, desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // umma_desc_sw128(0), split in words
+        const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t act_lo = desc_lo0 + (act_addr >> 4), ring_lo = desc_lo0 + (ring_addr >> 4), slot_lo = (uint32_t)sch.slot_bytes >> 4;
+        uint32_t slot = 0, use = 0, ready = 0, step_no = 0;
+        for (int it = -1; it < n_my; ++it) {
+            for (int si = 0; si < n_segs; ++si) {
+                const Tc4Seg sg = sch.segs[si];
+                const int tl = it + ((sg.flags & TC4_F_OFF) ? 1 : 0);
+                if (tl < 0 || tl >= n_my) { continue; }
+                const uint32_t par = (uint32_t)tl & 1u;
+                if (sg.flags & TC4_F_WAIT_IN) mbar_spin(bar_inready, par);
+                if (sg.wait[0] >= 0) mbar_spin(bar_done + 8 * sg.wait[0], par);
+                if (sg.wait[1] >= 0) mbar_spin(bar_done + 8 * sg.wait[1], par);
+                if (sg.wait_prev >= 0 && tl > 0) mbar_spin(bar_done + 8 * sg.wait_prev, par ^ 1u);
+                const uint32_t idesc = idesc0 | ((uint32_t)(sg.rows >> 2) << 17);                 // N = 2 rows, field = N >> 3
+                const uint32_t d_tmem = tmem_base + sg.tcol;
+                uint32_t acc = (sg.flags & TC4_F_ACC0) ? 0u : 1u;
+                const int kb_last = sg.kb1 - 1;
+                for (int kb = sg.kb0; kb <= kb_last; ++kb) {
+                    // Weights of this step landed in both CTAs?  A single mbarrier test costs ~150 cycles of latency even when the
+                    // phase is complete (scripts/umma3_bench.cu part E) -- as much as the 4 MMAs of a step take -- so the warp
+                    // tests ALL ring slots in one instruction (lane l: the slot of the l-th next step) and then issues every step
+                    // of the contiguous ready prefix without looking at the barriers again.
+                    if (ready == 0) {
+                        if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0 && step_no < 240) dbg[480 + step_no] = clock64();
+                        uint32_t s2 = slot + (uint32_t)lane, u2 = use;
+                        if (s2 >= (uint32_t)n_slots) { s2 -= (uint32_t)n_slots; ++u2; }
+                        uint32_t mask;
+                        do {
+                            const bool ok = lane < n_slots && mbar_test(bar_full + 8 * s2, u2 & 1u);
+                            mask = __ballot_sync(0xffffffffu, ok);
+                        } while (!(mask & 1u));
+                        ready = (uint32_t)__ffs((int)~mask) - 1u;
+                        tc_fence_after();
+                        if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0 && step_no < 240) dbg[240 + step_no] = ready;
+                    }
+                    --ready;
+                    if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0 && step_no < 240) dbg[step_no] = clock64();
+                    if (DBG == 1) ++step_no;
+                    const uint32_t a_lo = act_lo + (uint32_t)kb * (TC_KB_BYTES >> 4), b_lo = ring_lo + slot * slot_lo;
+                    const int lo = kb == sg.kb0 ? sg.ks_lo : 0, hi = kb == kb_last ? sg.ks_hi : 4;
+                    if (leader_lane && !(dflags & 4)) {
+                        if (lo == 0 && hi == 4) {
+                            umma2_f16_lo(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
+                            umma2_f16_lo(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                            umma2_f16_lo(d_tmem, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                            umma2_f16_lo(d_tmem, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                        } else {
+                            uint32_t a2 = acc;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks >= lo && ks < hi) { umma2_f16_lo(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, a2); a2 = 1u; }
+                        }
+                    }
+                    acc = 1u;
+                    if (leader_lane) umma2_commit_mc(bar_empty + 8 * slot, 3);                     // frees the slot in both CTAs
+                    __syncwarp();
+                    if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
+                }
+                if (leader_lane) {
+                    if (sg.commit >= 0) umma2_commit_mc(bar_tfull + 8 * sg.commit, 3);
+                    if (sg.flags & TC4_F_KBFREE) umma2_commit_mc(bar_kbfree, 3);
+                }
+                __syncwarp();
+            }
+            if (DBG == 1) step_no = 0;
+        }
+    } else if (warp == TC4_W_LOADER) {
+        // ===================== input loader: the pre-pass image of the next tile's leading K-blocks =====================
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)sch.pre_kb * TC_KB_BYTES;
+            const uint32_t leader_inready = mapa_u32(bar_inready, 0);
+            for (int i = 0; i < n_my; ++i) {
+                if (i > 0) mbar_wait(bar_kbfree, (uint32_t)(i - 1) & 1u);
+                const int pt = pt0 + i * pt_step;
+                mbar_expect_tx(bar_infull, bytes);
+                bulk_g2s(smem_u32(act), sch.pre_img + ((size_t)pt * 2 + crank) * bytes, bytes, bar_infull);
+                mbar_wait(bar_infull, (uint32_t)i & 1u);
+                mbar_arrive_cluster(leader_inready);
+            }
+        }
+    } else if (warp == TC4_W_FWD) {
+        // ===================== forwarder (peer): "chunk drained by my 16 epilogue warps" -> leader =====================
+        if (lane == 0 && crank == 1) {
+            const uint32_t leader_done = mapa_u32(bar_done, 0);
+            for (int it = -1; it < n_my; ++it)
+                for (int ci = 0; ci < n_chunks; ++ci) {
+                    const int tl = it + sch.chunks[ci].off;
+                    if (tl < 0 || tl >= n_my) continue;
+                    mbar_wait(bar_ldone + 8 * ci, (uint32_t)tl & 1u);
+                    mbar_arrive_cluster(leader_done + 8 * ci);
+                }
+        }
+    } else if (warp >= TC4_EW0 && warp < TC4_EW0 + TC4_NEW) {
+        // ===================== epilogue: thread = (column of the CTA, 8 consecutive features) =====================
+        const int ew = warp - TC4_EW0, qd = warp & 3, sub = ew >> 2, hh = qd >> 1;
+        const int r = (qd & 1) * 32 + lane;                          // my column = row of the activation K-blocks
+        const int gcol = (int)crank * 64 + r, pp = gcol / S, ps = gcol - pp * S;
+        const int src_lane = lane - ps;
+        const uint32_t act_row = smem_u32(act) + (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
+        const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const uint32_t my_done = crank == 0 ? bar_done : bar_ldone;
+        const int no = sch.n_out, ohalf = sch.out_pad / 2;
+        for (int it = -1; it < n_my; ++it) {
+            for (int ci = 0; ci < n_chunks; ++ci) {
+                const Tc4Chunk ch = sch.chunks[ci];
+                const int tl = it + ch.off;
+                if (tl < 0 || tl >= n_my) continue;
+                const int nu = ch.units[hh];
+                float x0 = 0.f;
+                const int row = (pt0 + tl * pt_step) * P2 + pp;
+                if (ch.kind == 1 && ps == 0) {                        // the kappa column of theta: ln f = x0 + ln10 NN(...)
+                    float xf[BT_MAX_D + 1];
+                    tc_load_column(fm, rows, M, row, xf);
+                    x0 = xf[0];
+                }
+                mbar_wait(bar_tfull + 8 * ci, (uint32_t)tl & 1u);
+                tc_fence_after();
+                if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && ew == 0 && lane == 0) dbg[1200 + 2 * ci] = clock64();
+                if (ch.kind == 0) {
+                    const uint32_t pos0 = ch.pos[hh];
+                    for (int u = (sub + ci) & 3; u < nu; u += 4) {
+                        float v[8];
+                        tmem_ld8(tlane + ch.tcol + 8u * (uint32_t)u, v);
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2)
+                            pk[j >> 1] = (dflags & 8) ? __float_as_uint(v[j]) : tc4_pack_bf16(tc4_act<S>(v[j], ps, src_lane), tc4_act<S>(v[j + 1], ps, src_lane));
+                        const uint32_t p = pos0 + 8u * (uint32_t)u;
+                        tc4_sts128(act_row + (p >> 6) * TC_KB_BYTES + ((((p >> 3) & 7u) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    fence_proxy_async();
+                } else {
+                    for (int u = (sub + ci) & 3; u < nu; u += 4) {
+                        float v[8];
+                        tmem_ld8(tlane + ch.tcol + 8u * (uint32_t)u, v);
+                        if (row < M) {
+                            float* dst = ps == 0 ? lf + (size_t)row * no : jac + ((size_t)row * (S - 1) + (ps - 1)) * no;
+                            const int o0 = hh * ohalf + 8 * u;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (o0 + j < no) dst[o0 + j] = v[j] + x0;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(my_done + 8 * ci);
+                if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && ew == 0 && lane == 0) dbg[1201 + 2 * ci] = clock64();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == TC4_W_ISSUER) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+static inline int tc4_launch(Tc4Net& t, const FmapDev& fm, const float* rows, int M, float* lf, float* jac, int sm_count,
+                             cudaStream_t stream) {
+    if (!t.ready || !t.sched.pre_img) return -1;
+    const int S = jac ? 1 + fm.T : 1;
+    if (S != 1 && S != 4) return -2;
+    const int P2 = 128 / S;
+    const int n_ptiles = (M + P2 - 1) / P2;
+    int g = 2 * n_ptiles;
+    const int gmax = (sm_count / 2) * 2;
+    if (g > gmax) g = gmax;
+    static const bool want_dbg = getenv("BT_TC_DEBUG") != nullptr;
+    long long* dbg = nullptr;
+    if (want_dbg && n_ptiles > sm_count) {
+        cudaMalloc(&dbg, 1280 * sizeof(long long));
+        cudaMemset(dbg, 0, 1280 * sizeof(long long));
+    }
+    t.sched.dbg = dbg;
+    t.sched.dbg_flags = getenv("BT_TC4_FLAGS") ? atoi(getenv("BT_TC4_FLAGS")) : 0;
+    const int ko = t.sched.dbg_flags;
+    cudaError_t err;
+#define TC4_LAUNCH(S_, D_)                                                                                                    \
+    do {                                                                                                                      \
+        err = cudaFuncSetAttribute(mlp_tc4_kernel<S_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes); \
+        if (err == cudaSuccess) mlp_tc4_kernel<S_, D_><<<g, TC4_THREADS, t.smem_bytes, stream>>>(t.sched, fm, rows, M, lf, jac); \
+    } while (0)
+    if (S == 1 && ko == 1) TC4_LAUNCH(1, 2);
+    else if (S == 1 && ko == 4) TC4_LAUNCH(1, 8);
+    else if (S == 1 && ko == 8) TC4_LAUNCH(1, 16);
+    else if (S == 1 && ko == 16) TC4_LAUNCH(1, 32);
+    else if (S == 1 && ko == 17) TC4_LAUNCH(1, 34);
+    else if (S == 1 && ko == 21) TC4_LAUNCH(1, 42);
+    else if (S == 1) { if (dbg) TC4_LAUNCH(1, 1); else TC4_LAUNCH(1, 0); }
+    else             { if (dbg) TC4_LAUNCH(4, 1); else TC4_LAUNCH(4, 0); }
+#undef TC4_LAUNCH
+    if (err != cudaSuccess) return -5;
+    if (cudaPeekAtLastError() != cudaSuccess) return -6;
+    if (dbg) {
+        static long long h[1280];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        t.sched.dbg = nullptr;
+        const long long t0 = h[0];
+        fprintf(stderr, "[tc4 timeline S=%d M=%d, second tile of pair 0, cycles since its first step]\n", S, M);
+        fprintf(stderr, "  step: weights requested (leader) / (peer) | issuer starts polling | issues the step (steps found ready)\n");
+        for (int i = 0; i < t.sched.n_steps && i < 240; ++i)
+            fprintf(stderr, "  %3d: %7lld %7lld | %7lld | %7lld (%lld)\n", i, h[720 + i] ? h[720 + i] - t0 : -1, h[960 + i] ? h[960 + i] - t0 : -1,
+                    h[480 + i] ? h[480 + i] - t0 : -1, h[i] - t0, h[240 + i]);
+        fprintf(stderr, "  epilogue warp 0 (chunk: accumulator seen, drained):");
+        for (int c = 0; c < t.sched.n_chunks; ++c) if (h[1200 + 2 * c]) fprintf(stderr, " %d:%lld,%lld", c, h[1200 + 2 * c] - t0, h[1201 + 2 * c] - t0);
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}
