@@ -16,8 +16,23 @@
 //     by the pre-pass for primal columns, zero for tangent columns) meet weight columns bf16(b) and bf16(b - bf16(b));
 //   * a block is cut into chunks of <= nc_max features with their own accumulators; chunk c's epilogue runs under
 //     chunk c+1's MMAs, and the first chunk of the next block starts on the K-blocks that are already complete;
-//   * the output layer rides as 16 (32) extra rows of the last chunk of the last hidden block over the K range they
-//     share and is finished by a short continuation (N = 16 MMAs onto the same TMEM columns);
+//   * the activations of the LAST hidden block are never stored: their only reader is the output layer.  The epilogue of
+//     those ("tail") chunks contracts them with the output weights itself, on the WARP-level tensor cores: a thread owns
+//     one column and 8 features, so the warp's 32 x 8 bf16 activations take one 16-byte store each into a 512-byte tile
+//     of the warp, one ldmatrix.x4 turns them into the A fragments of four mma.sync.m16n8k8 (32 columns x 16 outputs,
+//     bf16 x bf16 -> f32), the B fragments are one 8-byte load per lane from a table in fragment order (14 KB, L1).  The
+//     partial sums (16 registers) ride through the block's chunks; its last chunk parks them in a staging area and the
+//     sub == 0 warps add the 8 partials of a column in a fixed order (deterministic).  The staging area is the tail of
+//     the activation buffer, dead once the tile's last MMA has completed; the readers zero what they read (padding
+//     positions must stay finite: they meet zero weights in the MMAs).  What did NOT work for this contraction
+//     (profiles/r02_microbench.txt): float32 FFMA2 against weights in shared memory (every 16-byte warp-uniform load
+//     still writes 512 B into the register file: 4 cycles each on the load-store unit, 10 k cycles per tile), the same
+//     from the constant bank (worse), 64-bit or 32-bit shared-memory atomics for the sums (~1.5 lane-operations per
+//     cycle).  Not storing the block removes a third of the activation buffer (55 of 168 KB for the reference
+//     architecture) -- which goes to the weight ring: 7 slots instead of 4; with 4 slots every step waited ~450 cycles
+//     for its weights whatever its size (round trip producer -> bulk copy -> relay -> issuer -> commit ~1.8 k cycles);
+//   * the output layer's rows over the OTHER features ride as 16 extra rows of the last chunk of the last hidden block,
+//     whose epilogue adds the two parts and stores ln f / the Jacobian;
 //   * the next tile's input K-blocks (pre-pass image, mlp_pre.cuh) are brought in by ONE bulk copy as soon as the last
 //     MMA reading them has completed.
 // The schedule is a flat list of steps (one weight chunk x one K-block = up to 4 MMAs) and a list of chunks built on
@@ -44,7 +59,8 @@
 #define TC4_MAX_STEPS 176
 #define TC4_MAX_CHUNKS 16
 #define TC4_MAX_SLOTS 8
-#define TC4_MISC_BYTES 1024
+#define TC4_MISC_BYTES (1024 + TC4_NEW * 512)    // barriers + one 32 x 8 bf16 transposition tile per epilogue warp
+#define TC4_OUT_PAD 16
 #define TC4_MAX_SEGS 64
 #define TC4_F_ACC0 1               // first MMA of the step overwrites the accumulator
 #define TC4_F_WAIT_IN 2            // wait for the tile's input K-blocks
@@ -75,10 +91,12 @@ struct Tc4Chunk {                  // 12 bytes, the epilogue's view
     uint16_t tcol;
     uint16_t pos[2];               // activation position of the first feature of each lane half
     uint8_t units[2];              // live 8-feature units per lane half
-    uint8_t kind;                  // 0: activation, 1: network outputs
+    uint8_t kind;                  // 0: activation, 2: tail (last hidden block: contracted with the output weights, pos = feature
+                                   //    offset within the block), 3: tail + the tile's outputs
     uint8_t off;                   // 1: belongs to the next tile of the iteration
-    uint8_t pad[2];
+    uint16_t ocol;                 // kind 3: TMEM column of the output rows that rode along
 };
+static_assert(sizeof(Tc4Chunk) == 12, "Tc4Chunk layout");
 struct Tc4Sched {
     int n_steps, n_segs, n_chunks, n_slots, slot_bytes, act_kb, n_out, out_pad, pre_kb, one_pos;
     // the lists live in the kernel's parameter (constant) bank: the MMA issuer's loop then runs on the uniform datapath
@@ -86,14 +104,20 @@ struct Tc4Sched {
     Tc4Seg segs[TC4_MAX_SEGS];
     Tc4Chunk chunks[TC4_MAX_CHUNKS];
     const uint8_t* wstream[2];
+    int no4;                       // ceil(n_out / 4)
+    int stage_kb;                  // first of the no4 activation K-blocks that double as the staging area of the tail sums
     const uint8_t* pre_img;
     long long* dbg;
     int dbg_flags;                 // DBG instantiation only (results invalid): 1 no weight copies, 2 relay does not wait, 4 no MMAs, 8 no activation math
+    const uint2* wfrag;            // output weights of the tail block as mma.m16n8k8 B fragments: [unit of 8 features][lane] x
+                                   // {outputs 0-7, outputs 8-15}, bf16 pairs (0.5 out_scale W_out)
 };
 struct Tc4Net {
     bool ready = false;
     Tc4Sched sched{};
     void* d_w[2] = {nullptr, nullptr};
+    uint2* d_wfrag = nullptr;
+    std::vector<float> h_wtail;    // the same weights as [feature][16] floats (bf16-rounded), for the host-side check
     size_t smem_bytes = 0;
     int n_pre = 0;
     double mma_cycles = 0;         // model: sum over MMAs of the measured cycles per instruction
@@ -104,6 +128,7 @@ struct Tc4Net {
 };
 static inline void tc4_free(Tc4Net& t) {
     for (int c = 0; c < 2; ++c) if (t.d_w[c]) cudaFree(t.d_w[c]);
+    if (t.d_wfrag) cudaFree(t.d_wfrag);
     t = Tc4Net();
 }
 static inline int tc4_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -128,13 +153,13 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
                                  int mode, bool upload) {
     t.ready = false;
     if (nc_max < 64 || nc_max > 256 || nc_max % 16) return 0;
-    if (n_blocks < 2 || n_blocks > BT_MAX_BLOCKS || n_out < 1 || n_out > 32 || n_feat0 > 64) return 0;
+    if (n_blocks < 2 || n_blocks > BT_MAX_BLOCKS || n_out < 1 || n_out > TC4_OUT_PAD || n_feat0 > 64) return 0;
     const int n_pre = tc4_choose_pre(n_feat0, n_blocks, block_new);
     if (n_pre < 1) return 0;
     Tc4Sched& s = t.sched;
     memset(&s, 0, sizeof s);
     t.n_pre = n_pre;
-    const int out_pad = tc4_round_up(n_out, 16);
+    const int out_pad = TC4_OUT_PAD;
     // ---- positions in the activation buffer
     std::vector<int> in_orig(n_blocks + 1), lpos(n_blocks, -1);
     in_orig[0] = n_feat0;
@@ -146,15 +171,21 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
     if (s.pre_kb > 3) return 0;
     int pos = tc4_round_up(pre_feats + 2, 16);
     for (int l = n_pre; l < n_blocks; ++l) { lpos[l] = pos; pos = tc4_round_up(pos + block_new[l], 16); }
-    const int n_pos = pos;
+    const int n_pos = lpos[n_blocks - 1];            // the last hidden block is not stored (tail chunks)
     s.act_kb = (n_pos + TC_BK - 1) / TC_BK;
+    s.no4 = (n_out + 3) / 4;
+    // staging of the tail sums: [8 holders][64 columns][4 no4] floats = no4 K-blocks at the end of the activation buffer.
+    // While it is in use the only other traffic on the buffer is the next tile's first block (its MMAs read the input
+    // K-blocks, its epilogue writes the block's own positions): the two must not overlap.
+    s.stage_kb = s.act_kb - s.no4;
+    if (s.stage_kb * TC_BK < tc4_round_up(lpos[n_pre] + block_new[n_pre], 16) || s.stage_kb < s.pre_kb) return 0;
     s.n_out = n_out;
     s.out_pad = out_pad;
     // position -> original feature (-1: padding, -2 / -3: constant one, high / low part of the bias)
     std::vector<int> orig(s.act_kb * TC_BK, -1);
     for (int k = 0; k < pre_feats; ++k) orig[k] = k;
     orig[one_pos] = -2; orig[one_pos + 1] = -3;
-    for (int l = n_pre; l < n_blocks; ++l) for (int f = 0; f < block_new[l]; ++f) orig[lpos[l] + f] = in_orig[l] + f;
+    for (int l = n_pre; l < n_blocks - 1; ++l) for (int f = 0; f < block_new[l]; ++f) orig[lpos[l] + f] = in_orig[l] + f;
     // ---- chunks
     struct RowSrc { int layer, row; };          // layer -1: output layer, -2: padding
     struct HChunk { int layer, n, cols, tcol, gelu_n, klo_pos, khi_pos; std::vector<RowSrc> rows[2]; };
@@ -193,17 +224,7 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
     }
     first_chunk[n_blocks] = (int)chunks.size();
     const int n_gelu_chunks = (int)chunks.size();
-    {   // output continuation: N = out_pad onto the columns of the output rows of the last chunk
-        HChunk h;
-        h.layer = -1; h.n = out_pad; h.cols = out_pad / 2; h.tcol = 0; h.gelu_n = 0;
-        h.klo_pos = lpos[n_blocks - 1]; h.khi_pos = n_pos;
-        for (int hh = 0; hh < 2; ++hh) {
-            h.rows[hh].assign(out_pad / 2, RowSrc{-2, 0});
-            for (int j = 0; j < out_pad / 2; ++j) if (hh * (out_pad / 2) + j < n_out) h.rows[hh][j] = RowSrc{-1, hh * (out_pad / 2) + j};
-        }
-        chunks.push_back(h);
-    }
-    const int n_chunks = (int)chunks.size();
+    const int n_chunks = n_gelu_chunks;
     if (n_chunks > TC4_MAX_CHUNKS) return 0;
     // ---- TMEM: blocks alternate between two regions, the chunk with the output rows has its own
     {
@@ -222,20 +243,12 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
                 else { chunks[c].tcol = col; col += chunks[c].cols; }
             }
         }
-        chunks[n_chunks - 1].tcol = r2 + chunks[n_gelu_chunks - 1].gelu_n / 2;
     }
     // ---- issue order of the chunks within one iteration (mode 1: first block of the next tile before the continuation)
     struct Item { int chunk, off; };
     std::vector<Item> order;
-    const int fb_end = first_chunk[n_pre + 1];           // chunks of the first block: [0, fb_end)
-    if (mode == 1 && fb_end < n_gelu_chunks) {
-        for (int c = fb_end; c < n_gelu_chunks; ++c) order.push_back({c, 0});
-        for (int c = 0; c < fb_end; ++c) order.push_back({c, 1});
-        order.push_back({n_chunks - 1, 0});
-    } else {
-        mode = 0;
-        for (int c = 0; c < n_chunks; ++c) order.push_back({c, 0});
-    }
+    (void)mode;                                          // (the cross-tile order died with the output continuation)
+    for (int c = 0; c < n_chunks; ++c) order.push_back({c, 0});
     // ---- steps, with the waits each one needs
     // Chunk c is "drained" (barrier done[c]) when every epilogue warp has read its accumulators and written + fenced its
     // features.  A step waits (a) for the chunks that wrote the features of its K-block, (b) before overwriting TMEM
@@ -257,7 +270,7 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
                 const int tile = it + im.off;
                 if (tile < 0) continue;
                 const HChunk& h = chunks[im.chunk];
-                const bool is_cont = h.layer == -1;
+                const bool is_cont = false;
                 const int kb0 = h.klo_pos / TC_BK, kb1 = (h.khi_pos + TC_BK - 1) / TC_BK;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     Tc4Step st;
@@ -273,6 +286,7 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
                     // (a) features of this K-block: written by chunks of THIS tile (positions < khi_pos only)
                     for (int c = 0; c < n_gelu_chunks; ++c) {
                         const HChunk& w = chunks[c];
+                        if (w.layer == n_blocks - 1) continue;            // tail chunks write no features
                         for (int hh = 0; hh < 2; ++hh) {
                             int cb = 0;
                             for (int cc = first_chunk[w.layer]; cc < c; ++cc) cb += chunks[cc].gelu_n;
@@ -285,7 +299,6 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
                     if (st.flags & TC4_F_ACC0)
                         for (int q = h.tcol; q < h.tcol + h.cols; ++q)
                             if (tm[q].chunk >= 0) need.push_back({tm[q].chunk, tm[q].tile});
-                    // the continuation accumulates onto columns owned by the last activation chunk of its own tile: no hazard
                     int nw = 0;
                     for (auto& nd : need) {
                         if (waited_tile[0][nd.first] >= nd.second || (im.off && waited_tile[1][nd.first] >= nd.second)) continue;
@@ -297,8 +310,7 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
                     if (kb == kb1 - 1) st.commit = (int8_t)im.chunk;
                     if (emit) { steps.push_back(st); step_chunk.push_back(im.chunk); step_kb.push_back(kb); }
                 }
-                if (!is_cont) for (int q = h.tcol; q < h.tcol + h.cols; ++q) tm[q] = Own{im.chunk, tile};
-                else for (int q = h.tcol; q < h.tcol + h.cols; ++q) tm[q] = Own{im.chunk, tile};
+                for (int q = h.tcol; q < h.tcol + h.cols; ++q) tm[q] = Own{im.chunk, tile};
             }
         }
     }
@@ -374,6 +386,32 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
             }
         }
     }
+    // ---- output weights of the tail block (activations are 2 x GELU: the factor 1/2 lives here), float32
+    {
+        const int lb = n_blocks - 1, nu = (block_new[lb] + 7) / 8;
+        std::vector<uint16_t> wb((size_t)nu * 8 * TC4_OUT_PAD, 0);
+        t.h_wtail.assign((size_t)nu * 8 * TC4_OUT_PAD, 0.f);
+        for (int f = 0; f < block_new[lb]; ++f)
+            for (int o = 0; o < n_out; ++o) {
+                const uint16_t h = f32_to_bf16_rne((float)(0.5 * out_scale * w_out[(size_t)o * n_feat + in_orig[lb] + f]));
+                wb[(size_t)f * TC4_OUT_PAD + o] = h;
+                uint32_t hb = (uint32_t)h << 16; float hf; memcpy(&hf, &hb, 4);
+                t.h_wtail[(size_t)f * TC4_OUT_PAD + o] = hf;
+            }
+        // B fragment of mma.m16n8k8 (col): lane t holds B[k = 2 (t % 4) + {0, 1}][n = t / 4]
+        std::vector<uint32_t> frag((size_t)nu * 32 * 2);
+        for (int u = 0; u < nu; ++u)
+            for (int l = 0; l < 32; ++l)
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int o = 8 * nt + l / 4, f = 8 * u + 2 * (l % 4);
+                    frag[((size_t)u * 32 + l) * 2 + nt] = (uint32_t)wb[(size_t)f * TC4_OUT_PAD + o] | ((uint32_t)wb[(size_t)(f + 1) * TC4_OUT_PAD + o] << 16);
+                }
+        if (upload) {
+            if (cudaMalloc(&t.d_wfrag, frag.size() * 4) != cudaSuccess) return -1;
+            if (cudaMemcpy(t.d_wfrag, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+            s.wfrag = t.d_wfrag;
+        }
+    }
     // ---- the epilogue's chunk list, in issue order
     std::vector<Tc4Chunk> ech;
     std::vector<int> order_pos(n_chunks, -1);
@@ -384,17 +422,19 @@ static inline int tc4_build_mode(Tc4Net& t, int n_feat0, int n_blocks, const int
         memset(&e, 0, sizeof e);
         e.tcol = (uint16_t)h.tcol;
         e.off = (uint8_t)im.off;
-        if (h.layer == -1) {
-            e.kind = 1;
-            e.units[0] = e.units[1] = (uint8_t)(out_pad / 16);
-        } else {
+        {
+            const bool tail = h.layer == n_blocks - 1;
             int cb = 0;
             for (int cc = first_chunk[h.layer]; cc < im.chunk; ++cc) cb += chunks[cc].gelu_n;
             for (int hh = 0; hh < 2; ++hh) {
                 const int f0 = cb + hh * (h.gelu_n / 2);
-                e.pos[hh] = (uint16_t)(lpos[h.layer] + f0);
+                e.pos[hh] = (uint16_t)(tail ? f0 : lpos[h.layer] + f0);
                 const int live = std::max(0, std::min(block_new[h.layer] - f0, h.gelu_n / 2));
                 e.units[hh] = (uint8_t)((live + 7) / 8);
+            }
+            if (tail) {
+                e.kind = im.chunk == n_chunks - 1 ? 3 : 2;
+                e.ocol = (uint16_t)(h.tcol + h.gelu_n / 2);
             }
         }
         ech.push_back(e);
@@ -491,6 +531,11 @@ __device__ __forceinline__ float tc4_act(float v, int s_col, int src_lane) {
     return ((1.f + t) + xc * (1.f - t * t) * du) * v;
 }
 
+__device__ __forceinline__ void tc4_mma_k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b));
+}
+
 template <int S, int DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC4_THREADS, 1)
 mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __restrict__ rows, int M, float* __restrict__ lf, float* __restrict__ jac) {
@@ -505,7 +550,9 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
     const uint32_t bar_done = smem_u32(bars + 32), bar_ldone = smem_u32(bars + 48);
     const uint32_t bar_infull = smem_u32(bars + 64), bar_inready = smem_u32(bars + 65), bar_kbfree = smem_u32(bars + 66);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the shuffle tells the compiler that the warp index is warp-uniform: role dispatch, schedule walks and the tail's
+    // constant-bank weight loads then run on the uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
     constexpr int P2 = 128 / S;                                      // rows of theta per pair-tile
     const int n_ptiles = (M + P2 - 1) / P2;
@@ -608,10 +655,12 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
                 const int tl = it + ((sg.flags & TC4_F_OFF) ? 1 : 0);
                 if (tl < 0 || tl >= n_my) { continue; }
                 const uint32_t par = (uint32_t)tl & 1u;
+                if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0) dbg[1300 + 4 * si] = clock64();
                 if (sg.flags & TC4_F_WAIT_IN) mbar_spin(bar_inready, par);
                 if (sg.wait[0] >= 0) mbar_spin(bar_done + 8 * sg.wait[0], par);
                 if (sg.wait[1] >= 0) mbar_spin(bar_done + 8 * sg.wait[1], par);
                 if (sg.wait_prev >= 0 && tl > 0) mbar_spin(bar_done + 8 * sg.wait_prev, par ^ 1u);
+                if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0) dbg[1301 + 4 * si] = clock64();
                 const uint32_t idesc = idesc0 | ((uint32_t)(sg.rows >> 2) << 17);                 // N = 2 rows, field = N >> 3
                 const uint32_t d_tmem = tmem_base + sg.tcol;
                 uint32_t acc = (sg.flags & TC4_F_ACC0) ? 0u : 1u;
@@ -657,11 +706,13 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
                     __syncwarp();
                     if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
                 }
+                if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0) dbg[1302 + 4 * si] = clock64();
                 if (leader_lane) {
                     if (sg.commit >= 0) umma2_commit_mc(bar_tfull + 8 * sg.commit, 3);
                     if (sg.flags & TC4_F_KBFREE) umma2_commit_mc(bar_kbfree, 3);
                 }
                 __syncwarp();
+                if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0) dbg[1303 + 4 * si] = clock64();
             }
             if (DBG == 1) step_no = 0;
         }
@@ -700,7 +751,12 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
         const uint32_t act_row = smem_u32(act) + (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
         const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
         const uint32_t my_done = crank == 0 ? bar_done : bar_ldone;
-        const int no = sch.n_out, ohalf = sch.out_pad / 2;
+        const int no = sch.n_out, no4 = sch.no4;
+        const uint32_t stage = smem_u32(act) + (uint32_t)sch.stage_kb * TC_KB_BYTES;   // [8 holders][64 columns][4 no4] floats
+        const uint32_t ttile = smem_u32(misc + 1024) + (uint32_t)ew * 512u + (uint32_t)lane * 16u;   // my row of the warp's tile
+        float tcf[4][4];                                              // tail sums: C fragments [16-column tile x 8-output tile]
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { tcf[q][0] = tcf[q][1] = tcf[q][2] = tcf[q][3] = 0.f; }
         for (int it = -1; it < n_my; ++it) {
             for (int ci = 0; ci < n_chunks; ++ci) {
                 const Tc4Chunk ch = sch.chunks[ci];
@@ -709,10 +765,17 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
                 const int nu = ch.units[hh];
                 float x0 = 0.f;
                 const int row = (pt0 + tl * pt_step) * P2 + pp;
-                if (ch.kind == 1 && ps == 0) {                        // the kappa column of theta: ln f = x0 + ln10 NN(...)
+                if (ch.kind == 3 && sub == 0 && ps == 0) {            // the kappa column of theta: ln f = x0 + ln10 NN(...)
                     float xf[BT_MAX_D + 1];
                     tc_load_column(fm, rows, M, row, xf);
                     x0 = xf[0];
+                }
+                uint2 bq[4];                                          // tail chunk: B fragments of my (at most 4) units, fetched
+                if (ch.kind != 0) {                                   // while the accumulators are still being computed
+                    const uint2* wf = sch.wfrag + (size_t)(ch.pos[hh] >> 3) * 32 + lane;
+                    const int u0 = (sub + ci) & 3;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) bq[k] = u0 + 4 * k < nu ? __ldg(wf + (u0 + 4 * k) * 32) : make_uint2(0u, 0u);
                 }
                 mbar_wait(bar_tfull + 8 * ci, (uint32_t)tl & 1u);
                 tc_fence_after();
@@ -731,14 +794,77 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
                     }
                     fence_proxy_async();
                 } else {
-                    for (int u = (sub + ci) & 3; u < nu; u += 4) {
+                    // tail chunk: 8 activations of my column x the output weights (warp-uniform 16-byte loads), added to the
+                    // column's 64-bit fixed-point accumulators (2^-32 resolution; integer adds commute, so the result does not
+                    // depend on which warp comes first)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int u = ((sub + ci) & 3) + 4 * k;
+                        if (u >= nu) break;
+                        const uint2 b = bq[k];
                         float v[8];
                         tmem_ld8(tlane + ch.tcol + 8u * (uint32_t)u, v);
-                        if (row < M) {
-                            float* dst = ps == 0 ? lf + (size_t)row * no : jac + ((size_t)row * (S - 1) + (ps - 1)) * no;
-                            const int o0 = hh * ohalf + 8 * u;
+                        uint32_t pk[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) if (o0 + j < no) dst[o0 + j] = v[j] + x0;
+                        for (int j = 0; j < 8; j += 2) pk[j >> 1] = tc4_pack_bf16(tc4_act<S>(v[j], ps, src_lane), tc4_act<S>(v[j + 1], ps, src_lane));
+                        __syncwarp();
+                        tc4_sts128(ttile, pk[0], pk[1], pk[2], pk[3]);
+                        __syncwarp();
+                        uint32_t a0, a1, a2, a3;                      // A fragments: columns [0, 16) and [16, 32) of the warp
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(ttile) : "memory");
+                        if (!(dflags & 64)) {
+                            tc4_mma_k8(tcf[0], a0, a1, b.x);
+                            tc4_mma_k8(tcf[1], a0, a1, b.y);
+                            tc4_mma_k8(tcf[2], a2, a3, b.x);
+                            tc4_mma_k8(tcf[3], a2, a3, b.y);
+                        }
+                    }
+                    if (ch.kind == 3) {
+                        // the tile's outputs: park my sums, then the sub == 0 warps add, per column, the rows of the output
+                        // layer that rode along in TMEM (features of the stored blocks) and the 8 partial tail sums
+                        const uint32_t ws = 16u * (uint32_t)no4;            // bytes per (holder, column)
+                        const uint32_t hold = stage + (uint32_t)((hh * 4 + sub) * 64 + (qd & 1) * 32) * ws;
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+                                const uint32_t o = 8u * nt + 2u * (lane & 3);
+                                float (&c)[4] = tcf[mt * 2 + nt];
+                                if (o < 4u * no4) {
+                                    const uint32_t a = hold + (uint32_t)(16 * mt + (lane >> 2)) * ws + o * 4u;
+                                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(c[0]), "f"(c[1]) : "memory");
+                                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + 8u * ws), "f"(c[2]), "f"(c[3]) : "memory");
+                                }
+                                c[0] = c[1] = c[2] = c[3] = 0.f;
+                            }
+                        asm volatile("bar.sync 1, %0;" ::"n"(TC4_NEW * 32) : "memory");
+                        if (sub == 0) {
+                            float v[8];
+                            tmem_ld8(tlane + ch.ocol, v);
+                            float* dst = ps == 0 ? lf + (size_t)row * no : jac + ((size_t)row * (S - 1) + (ps - 1)) * no;
+#pragma unroll
+                            for (int q2 = 0; q2 < 2; ++q2) {                  // my 8 outputs = two groups of 4
+                                const int q = hh * 2 + q2;
+                                if (q < no4) {
+                                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                    for (int h = 0; h < 8; ++h) {
+                                        const uint32_t cell = stage + ((uint32_t)(h * 64 + r) * (uint32_t)no4 + (uint32_t)q) * 16u;
+                                        float4 pz;
+                                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pz.x), "=f"(pz.y), "=f"(pz.z), "=f"(pz.w) : "r"(cell) : "memory");
+                                        tc4_sts128(cell, 0u, 0u, 0u, 0u);
+                                        sum.x += pz.x; sum.y += pz.y; sum.z += pz.z; sum.w += pz.w;
+                                    }
+                                    const int o = 4 * q;
+                                    if (row < M) {
+                                        if (o < no) dst[o] = v[4 * q2] + sum.x + x0;
+                                        if (o + 1 < no) dst[o + 1] = v[4 * q2 + 1] + sum.y + x0;
+                                        if (o + 2 < no) dst[o + 2] = v[4 * q2 + 2] + sum.z + x0;
+                                        if (o + 3 < no) dst[o + 3] = v[4 * q2 + 3] + sum.w + x0;
+                                    }
+                                }
+                            }
+                            fence_proxy_async();
                         }
                     }
                 }
@@ -771,8 +897,8 @@ static inline int tc4_launch(Tc4Net& t, const FmapDev& fm, const float* rows, in
     static const bool want_dbg = getenv("BT_TC_DEBUG") != nullptr;
     long long* dbg = nullptr;
     if (want_dbg && n_ptiles > sm_count) {
-        cudaMalloc(&dbg, 1280 * sizeof(long long));
-        cudaMemset(dbg, 0, 1280 * sizeof(long long));
+        cudaMalloc(&dbg, 1600 * sizeof(long long));
+        cudaMemset(dbg, 0, 1600 * sizeof(long long));
     }
     t.sched.dbg = dbg;
     t.sched.dbg_flags = getenv("BT_TC4_FLAGS") ? atoi(getenv("BT_TC4_FLAGS")) : 0;
@@ -789,13 +915,15 @@ static inline int tc4_launch(Tc4Net& t, const FmapDev& fm, const float* rows, in
     else if (S == 1 && ko == 16) TC4_LAUNCH(1, 32);
     else if (S == 1 && ko == 17) TC4_LAUNCH(1, 34);
     else if (S == 1 && ko == 21) TC4_LAUNCH(1, 42);
+    else if (S == 1 && ko == 32) TC4_LAUNCH(1, 64);
+    else if (S == 1 && ko == 96) TC4_LAUNCH(1, 192);
     else if (S == 1) { if (dbg) TC4_LAUNCH(1, 1); else TC4_LAUNCH(1, 0); }
     else             { if (dbg) TC4_LAUNCH(4, 1); else TC4_LAUNCH(4, 0); }
 #undef TC4_LAUNCH
     if (err != cudaSuccess) return -5;
     if (cudaPeekAtLastError() != cudaSuccess) return -6;
     if (dbg) {
-        static long long h[1280];
+        static long long h[1600];
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
         cudaFree(dbg);
@@ -806,6 +934,10 @@ static inline int tc4_launch(Tc4Net& t, const FmapDev& fm, const float* rows, in
         for (int i = 0; i < t.sched.n_steps && i < 240; ++i)
             fprintf(stderr, "  %3d: %7lld %7lld | %7lld | %7lld (%lld)\n", i, h[720 + i] ? h[720 + i] - t0 : -1, h[960 + i] ? h[960 + i] - t0 : -1,
                     h[480 + i] ? h[480 + i] - t0 : -1, h[i] - t0, h[240 + i]);
+        fprintf(stderr, "  issuer per segment: start / waits done / MMAs issued / commits done\n");
+        for (int i = 0; i < t.sched.n_segs; ++i)
+            fprintf(stderr, "  seg %2d (kb %d-%d rows %d): %7lld %7lld %7lld %7lld\n", i, t.sched.segs[i].kb0, t.sched.segs[i].kb1, t.sched.segs[i].rows,
+                    h[1300 + 4 * i] - t0, h[1301 + 4 * i] - t0, h[1302 + 4 * i] - t0, h[1303 + 4 * i] - t0);
         fprintf(stderr, "  epilogue warp 0 (chunk: accumulator seen, drained):");
         for (int c = 0; c < t.sched.n_chunks; ++c) if (h[1200 + 2 * c]) fprintf(stderr, " %d:%lld,%lld", c, h[1200 + 2 * c] - t0, h[1201 + 2 * c] - t0);
         fprintf(stderr, "\n");

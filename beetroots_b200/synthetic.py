@@ -44,6 +44,8 @@ class SyntheticProblem:
     H: int
     W: int
     sampler_kwargs: dict
+    a0: Optional[np.ndarray] = None      # (L,) centres / radii (log10) of the likelihood's mixing window,
+    a1: Optional[np.ndarray] = None      # the columns a0_best / a1_best of the reference's best_params.csv
 
 
 def smooth_theta_map(H: int, W: int, seed: int = 1, amplitude: float = 1.1) -> np.ndarray:
@@ -109,4 +111,4 @@ def make_problem(
     theta_init = theta_true + init_jitter * np.random.default_rng(seed_obs + 2).standard_normal((N, D))
     kw = dict(initial_step_size=1e-4, extreme_grad=1e-5, history_weight=0.99,
               selection_probas=[0.5, 0.5], k_mtm=k_mtm)
-    return SyntheticProblem(post, theta_true, theta_init, H, W, kw)
+    return SyntheticProblem(post, theta_true, theta_init, H, W, kw, a0, a1)

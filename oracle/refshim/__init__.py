@@ -7,11 +7,24 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = "/root/reference"
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the reference tree (build container) or its unmodified git-ignored copy that travels to the GPU box
+# (baseline/_ref, made by oracle/install_reference.py)
+_CANDIDATES = ("/root/reference", os.path.join(_REPO, "baseline", "_ref"))
+
+
+def reference_root():
+    for p in _CANDIDATES:
+        if os.path.isdir(os.path.join(p, "beetroots")):
+            return p
+    return None
+
+
+REFERENCE_ROOT = reference_root() or _CANDIDATES[0]
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "beetroots"))
+    return reference_root() is not None
 
 
 def install():
@@ -19,12 +32,12 @@ def install():
     import numpy as np
 
     if not reference_available():
-        raise RuntimeError("the reference tree is only present in the build container")
+        raise RuntimeError("no reference tree: neither /root/reference nor baseline/_ref (oracle/install_reference.py)")
     if not hasattr(np, "infty"):
         np.infty = np.inf                                   # my_sampler.py:277,372,379
     sys.modules.setdefault("h5py", types.ModuleType("h5py"))  # abstract_saver.py:5
     here = os.path.dirname(os.path.abspath(__file__))
-    for p in (here, REFERENCE_ROOT):
+    for p in (here, reference_root()):
         if p not in sys.path:
             sys.path.insert(0, p)
     from beetroots.sampler.abstract_sampler import Sampler   # noqa: E402

@@ -105,7 +105,7 @@ static int check(int n_layers, double growing, int n_out, int nc_max, int mode) 
         tm[0].assign(512, 0.0); tm[1].assign(512, 0.0);
         std::vector<int> own(512, -1), own_tile(512, -1);
         std::vector<int> waited(s.n_chunks, -1000);
-        std::vector<double> out(32, 0.0);
+        std::vector<double> out(32, 0.0), tail(32, 0.0);
         const int n_my = 3;
         for (int it = -1; it < n_my; ++it) {
             for (int si = 0; si < s.n_steps; ++si) {
@@ -142,12 +142,15 @@ static int check(int n_layers, double growing, int n_out, int nc_max, int mode) 
                             for (int j = 0; j < 8; ++j) {
                                 const double v = tm[hh][ch.tcol + 8 * u + j];
                                 if (ch.kind == 0) { const int p = ch.pos[hh] + 8 * u + j; act[p] = gelu2(v); writer[p] = st.commit; writer_tile[p] = tl; }
-                                else { const int o = hh * (s.out_pad / 2) + 8 * u + j; if (o < n_out) out[o] = v; }
+                                else { const int f = ch.pos[hh] + 8 * u + j; for (int o = 0; o < 16; ++o) tail[o] += (double)t.h_wtail[(size_t)f * 16 + o] * gelu2(v); }
                             }
+                    if (ch.kind == 3)
+                        for (int hh = 0; hh < 2; ++hh)
+                            for (int j = 0; j < 8; ++j) { const int o = hh * 8 + j; if (o < n_out) out[o] = tm[hh][ch.ocol + j] + tail[o]; tail[o] = 0.0; }
                     for (int q = ch.tcol; q < ch.tcol + (ch.kind == 0 ? 0 : 0); ++q) (void)q;
                     // ownership of the accumulator columns (whole chunk, as the issuer sees it)
                     for (int q = st.tcol; q < st.tcol + n2; ++q) { own[q] = st.commit; own_tile[q] = tl; }
-                    if (ch.kind == 1) {
+                    if (ch.kind == 3) {
                         double e = 0;
                         for (int o = 0; o < n_out; ++o) e = std::max(e, fabs(out[o] - ref[o]));
                         if (e > 1e-9 * (1 + fabs(ref[0]))) { if (bad++ < 5) printf("  output mismatch tile %d: max abs %.3e (ref[0] %.4f out[0] %.4f)\n", tl, e, ref[0], out[0]); }
@@ -162,9 +165,9 @@ static int check(int n_layers, double growing, int n_out, int nc_max, int mode) 
 
 int main() {
     int bad = 0;
-    for (int mode = 0; mode < 2; ++mode) {
-        for (int nc : {128, 160, 192, 256}) bad += check(10, 0.5, 10, nc, mode);
-        bad += check(10, 0.5, 32, 160, mode);
+    for (int mode = 0; mode < 1; ++mode) {
+        for (int nc : {128, 160, 192, 224, 256}) bad += check(10, 0.5, 10, nc, mode);
+        bad += check(10, 0.5, 16, 160, mode);
         bad += check(7, 0.5, 5, 160, mode);
         bad += check(6, 1.0, 7, 160, mode);
         bad += check(9, 0.5, 3, 160, mode);
