@@ -13,6 +13,7 @@
 #include "../beetroots_b200/csrc/common.cuh"
 #include "../beetroots_b200/csrc/mlp_simt.cuh"
 #include "../beetroots_b200/csrc/mlp_tc3.cuh"
+#include "../beetroots_b200/csrc/mlp_tc4.cuh"
 
 // ---------------------------------------------------------------- A: rate
 template <int NACC, int PAT>
@@ -386,8 +387,122 @@ template <int MMAS> static void run_ring(int n_slots, int n_prod, int n_wait, in
     cudaFree(d);
 }
 
+
+// ---------------------------------------------------------------- F: the tc4 issuer loop in isolation
+// issuer (warp IW of the leader): ballot-poll of all ring slots, then 4 MMAs (N) + commit per ready step, exactly like
+// mlp_tc4.cuh; producers (warps 1..NP, lane 0): spin empty[s] -> arrive full[s].  Variants (var bits): 1 = commit only after
+// every second step, 2 = no __syncwarp per step, 4 = producers use try_wait, 8 = single elected lane runs the whole loop
+// with per-step test_wait
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(832, 1)
+iss_k(long long* out, int iters, int n_slots, int n_prod, int N, int var, int iw) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar[24];
+    __shared__ uint32_t tptr;
+    for (int i = threadIdx.x; i < (131072 + 65536) / 16; i += 832) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    if (threadIdx.x == 0) { for (int i = 0; i < 24; ++i) mbar_init(smem_u32(&bar[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tptr)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
+    const uint32_t tb = tptr;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t full = smem_u32(&bar[0]), empty = smem_u32(&bar[8]), fin = smem_u32(&bar[17]);
+    if (cluster_ctarank() == 0) {
+        if (warp == iw) {
+            const bool leader = elect_one();
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 131072);
+            const uint32_t desc_lo0 = 1u << 16, desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t act_lo = desc_lo0 + (a0 >> 4), ring_lo = desc_lo0 + (b0 >> 4), slot_lo = 8192u >> 4;
+            uint32_t slot = 0, use = 0, ready = 0;
+            const long long t0 = clock64();
+            if (var & (8 | 128)) {
+                if (leader) {
+                    for (int i = 0; i < iters; ++i) {
+                        if (!(var & 128)) mbar_spin(full + 8 * slot, use & 1u);
+                        tc_fence_after();
+                        const uint32_t a_lo = act_lo + (uint32_t)(i & 15) * 512u, b_lo = ring_lo + slot * slot_lo;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma2_f16_lo(tb, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+                        umma2_commit_mc(empty + 8 * slot, 3);
+                        if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
+                    }
+                }
+                __syncwarp();
+            } else {
+                for (int i = 0; i < iters; ++i) {
+                    if (ready == 0 && !(var & 48)) {
+                        uint32_t s2 = slot + (uint32_t)lane, u2 = use;
+                        if (s2 >= (uint32_t)n_slots) { s2 -= (uint32_t)n_slots; ++u2; }
+                        uint32_t mask;
+                        do {
+                            const bool ok = lane < n_slots && mbar_test(full + 8 * s2, u2 & 1u);
+                            mask = __ballot_sync(0xffffffffu, ok);
+                        } while (!(mask & 1u));
+                        ready = (uint32_t)__ffs((int)~mask) - 1u;
+                        tc_fence_after();
+                    }
+                    --ready;
+                    const uint32_t a_lo = act_lo + (uint32_t)(i & 15) * 512u, b_lo = ring_lo + slot * slot_lo;
+                    if (var & 64) {
+                        if (leader) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma2_f16_lo(tb, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+                            umma2_commit_mc(empty + 8 * slot, 3);
+                        }
+                    } else {
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma2_f16_lo(tb, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+                    }
+                    if (leader && (!(var & 1) || (slot & 1u) || slot == (uint32_t)n_slots - 1)) {
+                        umma2_commit_mc(empty + 8 * slot, 3);
+                        if ((var & 1) && (slot & 1u)) umma2_commit_mc(empty + 8 * (slot - 1), 3);
+                    }
+                    }
+                    if (!(var & 2)) __syncwarp();
+                    if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
+                }
+            }
+            const long long t1 = clock64();
+            if (blockIdx.x == 0 && lane == 0) out[0] = t1 - t0;
+            if (leader) umma2_commit_mc(fin, 1);
+            __syncwarp();
+            mbar_wait(fin, 0);
+        } else if (warp >= 1 && warp <= n_prod && !(var & 16)) {
+            if (lane == 0) {
+                uint32_t slot = 0, use = 0;
+                for (int i = 0; i < iters; ++i) {
+                    if (i % n_prod == warp - 1) {
+                        if (use > 0) { if (var & 4) mbar_wait(empty + 8 * slot, (use - 1) & 1u); else mbar_spin(empty + 8 * slot, (use - 1) & 1u); }
+                        mbar_arrive(full + 8 * slot);
+                    }
+                    if (++slot == (uint32_t)n_slots) { slot = 0; ++use; }
+                }
+            }
+        }
+    }
+    tc_fence_before(); __syncthreads(); cluster_sync_all();
+    if (threadIdx.x < 32) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512)); }
+}
+static void run_iss(int n_slots, int n_prod, int N, int var, int iw) {
+    long long* d; cudaMalloc(&d, 16);
+    const int iters = 2000, smem = 131072 + 65536 + 2048;
+    cudaFuncSetAttribute(iss_k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    iss_k<<<148, 832, smem>>>(d, iters, n_slots, n_prod, N, var, iw);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("F issuer loop: %d slots, %d producers, N = %3d (%3d MMA cycles per step), variant %2d, issuer warp %2d: %.0f cycles per step  (%s)\n", n_slots, n_prod, N, N,
+           var, iw, (double)h / iters, cudaGetErrorString(e));
+    cudaFree(d);
+}
+
 int main(int argc, char** argv) {
     const int what = argc > 1 ? atoi(argv[1]) : 7;
+    setvbuf(stdout, nullptr, _IONBF, 0);
     if (what & 2) {
         run_layout(32, 0, 0);
         run_layout(64, 16, 24);      // continuation of "rows" [24, 32) and [56, 64) of a 64-wide accumulator by an N = 16 MMA at column 24
@@ -406,6 +521,9 @@ int main(int argc, char** argv) {
         for (int arr = 0; arr < 4; ++arr) { run_ring<0>(1, 1, 0, 0, arr); run_ring<0>(5, 4, 0, 0, arr); }
         run_ring<0>(1, 1, 0, 1, 0); run_ring<0>(1, 1, 0, 1, 2); run_ring<0>(8, 4, 0, 0, 0); run_ring<0>(8, 4, 16, 0, 0);
         run_ring<1>(1, 1, 0, 0, 0); run_ring<1>(5, 4, 0, 0, 0); run_ring<1>(8, 4, 0, 0, 0); run_ring<1>(8, 4, 16, 0, 0); run_ring<1>(8, 4, 16, 1, 0); run_ring<1>(8, 4, 0, 0, 1);
+    }
+    if (what & 32) {
+        for (int N : {144, 16}) { for (int var : {16, 16 + 64, 16 + 2, 16 + 64 + 2, 16 + 128}) run_iss(7, 4, N, var, 24); run_iss(7, 4, N, 16, 0); run_iss(7, 4, N, 16 + 64, 0); }
     }
     if (what & 8) {
         run_commit<0>("no commit");
