@@ -79,6 +79,8 @@ SIGNATURES = {
     "bt_mtm_optim_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "bt_mlp_kernel_variant": (C.c_int, [C.c_void_p]),
     "bt_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "bt_kernel_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_int64_p]),
+    "bt_reserve_scratch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "bt_mlp_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int64_p, c_int64_p]),
 }
 

@@ -8,7 +8,9 @@ SRC = os.path.join(HERE, "csrc", "bt_api.cu")
 OUT = os.path.join(HERE, "libbeetroots_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-shared", "-Xcompiler", "-fPIC", "-lcuda"]
+         "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-lcuda"]
+# extra defines for experiment builds, e.g. BT_NVCC_DEFS="-DBT_KNOCKOUTS" (compile-time knock-outs of the tensor-core kernels)
+FLAGS += os.environ.get("BT_NVCC_DEFS", "").split()
 
 
 def needs_build() -> bool:

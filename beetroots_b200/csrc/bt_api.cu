@@ -6,6 +6,7 @@
 #include <string.h>
 #include <math.h>
 #include <string>
+#include <thread>
 #include <vector>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -88,8 +89,16 @@ struct bt_ctx {
     float* tmpf = nullptr;              // N * max(D, L) float staging
     double* tmpd = nullptr;             // reductions
     uint8_t* owned_dev = nullptr;
-    // host staging
-    std::vector<float> hf;
+    // host staging: pinned, grown on demand
+    float* hpin = nullptr;
+    size_t hpin_cap = 0;
+    // per-kernel device timers of the HBM-bound kernels (bt_kernel_profile)
+    bool kprof = false;
+    std::vector<cudaEvent_t> kp_events;
+    std::vector<int> kp_ids;
+    size_t kp_used = 0;
+    double kp_ms[BT_KP_COUNT] = {0}, kp_bytes[BT_KP_COUNT] = {0};
+    int64_t kp_n[BT_KP_COUNT] = {0};
     // profiling of the forward-map kernel
     bool prof = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -174,6 +183,8 @@ extern "C" int bt_ctx_destroy(bt_ctx* c) {
                     c->tmpf, c->tmpd, c->owned_dev, c->mc_clppd, c->mc_pvy, c->mc_pvl, c->chain, c->snap_theta, c->snap_nll, c->snap_grad, c->snap_lf, c->colsum, c->acc_list, c->acc_count, c->cub_tmp};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->kp_events) cudaEventDestroy(e);
+    if (c->hpin) cudaFreeHost(c->hpin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -184,7 +195,11 @@ extern "C" int bt_set_stream(bt_ctx* c, uint64_t s) { REQUIRE(c, "null ctx"); c-
 extern "C" int bt_set_mlp_mode(bt_ctx* c, int mode) {
     REQUIRE(c, "null ctx");
     REQUIRE(mode == BT_MLP_FP32 || mode == BT_MLP_BF16_TC, "unknown mlp mode");
-    if (mode == BT_MLP_BF16_TC) REQUIRE(c->tc.ready, "tensor-core weights not available (upload the network first)");
+    if (mode == BT_MLP_BF16_TC) {
+        REQUIRE(c->tc.ready, "tensor-core weights not available (upload the network first)");
+        // every tensor-core kernel packs a row with its forward-mode tangents into S = 1 + T columns of a tile, S = 1 or 4
+        REQUIRE(!c->have_fm || c->fm.T == 3, "the tensor-core forward map needs exactly 3 sampled network inputs (T = 3); use BT_MLP_FP32");
+    }
     c->mlp_mode = mode;
     return 0;
 }
@@ -305,6 +320,7 @@ extern "C" int bt_upload_forward_map(bt_ctx* c, int d_full, const double* fixed,
         fm.fixed[idx[d]] = 0.f;    // sampled entries start from 0 (neural_network_approx.py:189-192)
         if (idx[d] >= 1) { REQUIRE(fm.T < BT_MAX_T, "too many sampled NN inputs"); fm.tslot[d] = fm.T; fm.tinput[fm.T] = idx[d] - 1; fm.T++; }
     }
+    REQUIRE(c->mlp_mode != BT_MLP_BF16_TC || fm.T == 3, "the tensor-core forward map needs exactly 3 sampled network inputs (T = 3); use BT_MLP_FP32");
     c->have_fm = true;
     return 0;
 }
@@ -379,18 +395,43 @@ extern "C" int bt_upload_graph(bt_ctx* c, const int32_t* nbr, int n_sites, const
 }
 
 // ---- state ------------------------------------------------------------------------------------
+// Host <-> device conversions of the float64 arrays of the reference API: pinned staging buffer, one asynchronous copy,
+// conversion split over a few host threads (a 1M-pixel map moves ~10^7 values per array).
+static int ensure_pinned(bt_ctx* c, size_t n) {
+    if (n <= c->hpin_cap) return 0;
+    if (c->hpin) { cudaFreeHost(c->hpin); c->hpin = nullptr; c->hpin_cap = 0; }
+    CK(cudaMallocHost(&c->hpin, (n + n / 8) * sizeof(float)));
+    c->hpin_cap = n + n / 8;
+    return 0;
+}
+template <typename F>
+static void host_parallel(size_t n, F f) {
+    const size_t grain = (size_t)1 << 18;
+    unsigned nt = (unsigned)std::min<size_t>((n + grain - 1) / grain, std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
+    if (nt <= 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t a = (size_t)t * per, b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=]() { f(a, b); });
+    }
+    for (auto& x : th) x.join();
+}
 static int h2d_from_double(bt_ctx* c, float* dst, const double* src, size_t n) {
-    c->hf.resize(n);
-    for (size_t i = 0; i < n; ++i) c->hf[i] = (float)src[i];
-    CK(cudaMemcpyAsync(dst, c->hf.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (ensure_pinned(c, n)) return -1;
+    float* h = c->hpin;
+    host_parallel(n, [=](size_t a, size_t b) { for (size_t i = a; i < b; ++i) h[i] = (float)src[i]; });
+    CK(cudaMemcpyAsync(dst, h, n * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
-static int d2h_to_double(bt_ctx* c, double* dst, const float* src, size_t n) {
-    c->hf.resize(n);
-    CK(cudaMemcpyAsync(c->hf.data(), src, n * 4, cudaMemcpyDeviceToHost, c->stream));
+static int d2h_to_double(bt_ctx* c, double* dst, const float* src, size_t n, const double* shift = nullptr, size_t n_shift = 1) {
+    if (ensure_pinned(c, n)) return -1;
+    CK(cudaMemcpyAsync(c->hpin, src, n * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < n; ++i) dst[i] = (double)c->hf[i];
+    const float* h = c->hpin;
+    if (shift) host_parallel(n, [=](size_t a, size_t b) { for (size_t i = a; i < b; ++i) dst[i] = (double)h[i] + shift[i % n_shift]; });
+    else host_parallel(n, [=](size_t a, size_t b) { for (size_t i = a; i < b; ++i) dst[i] = (double)h[i]; });
     return 0;
 }
 
@@ -398,7 +439,12 @@ extern "C" int bt_set_state(bt_ctx* c, const double* theta, const double* v, con
     REQUIRE(c, "null ctx");
     CK(cudaSetDevice(c->device));
     const size_t nd = (size_t)c->N * c->D;
-    if (theta) { for (size_t i = 0; i < nd; ++i) REQUIRE(!isnan(theta[i]), "Theta contains NaN"); if (h2d_from_double(c, c->theta, theta, nd)) return -1; }
+    if (theta) {
+        bool has_nan = false;
+        for (size_t i = 0; i < nd && !has_nan; ++i) has_nan = isnan(theta[i]);
+        REQUIRE(!has_nan, "Theta contains NaN");
+        if (h2d_from_double(c, c->theta, theta, nd)) return -1;
+    }
     if (v && h2d_from_double(c, c->v, v, nd)) return -1;
     if (j) { CK(cudaMemcpyAsync(c->jt, j, nd * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
     return 0;
@@ -526,6 +572,66 @@ extern "C" int bt_mlp_profile(bt_ctx* c, int enable, int reset, double* ms, int6
     return 0;
 }
 
+// ---- per-kernel timers of the memory-bound kernels ---------------------------------------------------------------------
+struct KpScope {
+    bt_ctx* c; bool on;
+    KpScope(bt_ctx* c_, int id, double bytes) : c(c_), on(c_->kprof) {
+        if (!on) return;
+        if (c->kp_used + 2 > c->kp_events.size())
+            for (int q = 0; q < 2; ++q) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; } c->kp_events.push_back(e); }
+        c->kp_ids.resize(c->kp_events.size() / 2);
+        c->kp_ids[c->kp_used / 2] = id;
+        c->kp_bytes[id] += bytes; c->kp_n[id]++;
+        cudaEventRecord(c->kp_events[c->kp_used], c->stream);
+    }
+    ~KpScope() { if (on) { cudaEventRecord(c->kp_events[c->kp_used + 1], c->stream); c->kp_used += 2; } }
+};
+extern "C" int bt_kernel_profile(bt_ctx* c, int enable, int reset, double* ms, double* bytes, int64_t* launches) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (c->kp_used) {
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t q = 0; q + 1 < c->kp_used; q += 2) {
+            float t_ms = 0;
+            CK(cudaEventElapsedTime(&t_ms, c->kp_events[q], c->kp_events[q + 1]));
+            c->kp_ms[c->kp_ids[q / 2]] += t_ms;
+        }
+        c->kp_used = 0;
+    }
+    for (int k = 0; k < BT_KP_COUNT; ++k) {
+        if (ms) ms[k] = c->kp_ms[k];
+        if (bytes) bytes[k] = c->kp_bytes[k];
+        if (launches) launches[k] = c->kp_n[k];
+        if (reset) { c->kp_ms[k] = 0; c->kp_bytes[k] = 0; c->kp_n[k] = 0; }
+    }
+    c->kprof = enable != 0;
+    return 0;
+}
+// bytes one pixel's stencil reads: its neighbour indices and their theta rows
+static inline double stencil_bytes(const bt_ctx* c) { return (double)c->max_degree * (4.0 + 4.0 * c->D); }
+
+extern "C" int bt_reserve_scratch(bt_ctx* c, int64_t max_rows, int64_t max_rows_jac) {
+    REQUIRE(c && c->have_net && c->have_fm, "upload the network and forward map first");
+    REQUIRE(max_rows >= 0 && max_rows_jac >= 0 && max_rows < ((int64_t)1 << 31), "bad row counts");
+    CK(cudaSetDevice(c->device));
+    if (max_rows_jac > max_rows) max_rows = max_rows_jac;
+    if (ensure_rows(c, (size_t)max_rows, false)) return -1;
+    if (max_rows_jac > 0 && ensure_rows(c, (size_t)max_rows_jac, true)) return -1;
+    const int variant = tc_variant(c);
+    if (variant == 4 || variant == 5) {
+        const int pre_kb = variant == 5 ? c->tc4.sched.pre_kb : c->tc3p.sched.pre_kb;
+        size_t need = pre_image_bytes((int)max_rows, 1, pre_kb);
+        if (max_rows_jac > 0) need = std::max(need, pre_image_bytes((int)max_rows_jac, 1 + c->fm.T, pre_kb));
+        if (need > c->pre_cap) {
+            if (c->pre_img) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->pre_img); c->pre_img = nullptr; c->pre_cap = 0; }
+            CK(cudaMalloc(&c->pre_img, need + need / 8));
+            c->pre_cap = need + need / 8;
+        }
+    }
+    if (!c->acc_list) { CK(cudaMalloc(&c->acc_list, (size_t)c->N * sizeof(int))); CK(cudaMalloc(&c->acc_count, sizeof(int))); }
+    return 0;
+}
+
 #define READY(c) REQUIRE((c) && (c)->have_net && (c)->have_fm && (c)->have_obs && (c)->have_graph && (c)->have_priors, \
                          "context not fully configured (network, forward map, observations, priors, graph)")
 
@@ -555,8 +661,7 @@ extern "C" int bt_get_current(bt_ctx* c, double* log_f, double* nll_pix, double*
     CK(cudaSetDevice(c->device));
     const size_t N = c->N, D = c->D, L = c->L;
     if (log_f) {
-        if (d2h_to_double(c, log_f, c->lf_cache, N * L)) return -1;
-        for (size_t i = 0; i < N * L; ++i) log_f[i] += c->shift[i % L];
+        if (d2h_to_double(c, log_f, c->lf_cache, N * L, c->shift.data(), L)) return -1;
     }
     if (nll_pix && d2h_to_double(c, nll_pix, c->nll_lik, N)) return -1;
     if (grad_lik && d2h_to_double(c, grad_lik, c->grad_lik, N * D)) return -1;
@@ -629,8 +734,7 @@ extern "C" int bt_forward_map(bt_ctx* c, int M, const double* theta, double* log
     const size_t D = c->D, L = c->L, T = c->fm.T;
     if (h2d_from_double(c, c->rows, theta, (size_t)M * D)) return -1;
     if (run_mlp(c, c->rows, M, c->lf_rows, grad_log_f ? c->jac_rows : nullptr)) return -1;
-    if (d2h_to_double(c, log_f, c->lf_rows, (size_t)M * L)) return -1;
-    for (size_t i = 0; i < (size_t)M * L; ++i) log_f[i] += c->shift[i % L];
+    if (d2h_to_double(c, log_f, c->lf_rows, (size_t)M * L, c->shift.data(), L)) return -1;
     if (grad_log_f) {
         std::vector<double> jac((size_t)M * (T > 0 ? T : 1) * L);
         if (T > 0 && d2h_to_double(c, jac.data(), c->jac_rows, (size_t)M * T * L)) return -1;
@@ -681,14 +785,22 @@ extern "C" int bt_pmala_site(bt_ctx* c, int site, double eps, double eta, double
     float *zd, *ud;
     if (stage_inject(c, z_inject, (size_t)c->N * c->D, &zd, tmp) || stage_inject(c, u_inject, c->N, &ud, tmp)) { free_tmp(c, tmp); return -1; }
     const int chromatic = c->n_sites > 1;
+    const double D4 = 4.0 * c->D, L4 = 4.0 * c->L;
+    {
+    KpScope kp(c, BT_KP_PMALA_PROPOSE, n_pix * (3 * D4 + 4 + stencil_bytes(c) + D4 + 8));   // theta, grad_lik, v, nll, stencil | row, logq, objc
     pmala_propose_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(c->pr, n_pix, sp, c->D, c->max_degree, c->theta, c->nbr,
         c->nll_lik, c->grad_lik, c->v, (float)eps, (float)eta, chromatic, seed, t, site, c->gid, zd, c->rows, c->logq, c->objc);
     KLAUNCH(c);
+    }
     if (run_mlp(c, c->rows, n_pix, c->lf_rows, c->jac_rows)) { free_tmp(c, tmp); return -1; }
+    // row, ln f, Jacobian, observation constants, stencil, v, j, logq, objc, nll, grad_lik | theta, v, j, nll, grad_lik, ln f cache, accept, log ratio
+    {
+    KpScope kp(c, BT_KP_PMALA_ACCEPT, n_pix * (D4 + L4 + c->fm.T * L4 + 48.0 * c->L + stencil_bytes(c) + 3 * D4 + 12 + D4 + 4 * D4 + 4 + L4 + 8));
     pmala_accept_kernel<<<(n_pix + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, n_pix, sp, c->D, c->L, c->max_degree,
         c->theta, c->nbr, c->obs, c->nll_lik, c->grad_lik, c->lf_cache, c->v, c->jt, c->rows, c->lf_rows, c->jac_rows,
         c->logq, c->objc, (float)eps, (float)eta, (float)alpha, chromatic, seed, t, site, c->gid, ud, c->accept, c->logpa);
     KLAUNCH(c);
+    }
     free_tmp(c, tmp);
     return 0;
 }
@@ -720,16 +832,26 @@ extern "C" int bt_mtm_site(bt_ctx* c, int site, int K, uint64_t seed, int64_t t,
     float *cd, *usd, *uad;
     if (stage_inject(c, cand_inject, (size_t)c->N * K * c->D, &cd, tmp) || stage_inject(c, usel_inject, c->N, &usd, tmp) ||
         stage_inject(c, uacc_inject, c->N, &uad, tmp)) { free_tmp(c, tmp); return -1; }
+    const double D4 = 4.0 * c->D, L4 = 4.0 * c->L, rowsK = (double)n_pix * K;
+    {
+    KpScope kp(c, BT_KP_MTM_GEN, rowsK * D4 + n_pix * (D4 + stencil_bytes(c)));              // candidate rows written | theta + stencil per pixel
     mtm_gen_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->pr, n_pix, sp, c->D, K, c->max_degree, c->theta,
         c->nbr, seed, t, site, c->gid, cd, c->rows);
     KLAUNCH(c);
+    }
     if (mtm_forward(c, n_pix, sp, K)) { free_tmp(c, tmp); return -1; }
     static const bool split_off = getenv("BT_MTM_NOSPLIT") != nullptr;
     if (c->max_degree <= 4 && !split_off) {
         // degree <= 4: weights by one thread per candidate row, then selection by one warp per pixel
+        {
+        // per candidate row: row + ln f read, weight written; per pixel: observation constants + stencil
+        KpScope kp(c, BT_KP_MTM_NL, (double)M * (D4 + L4 + 4) + n_pix * (48.0 * c->L + stencil_bytes(c)));
         mtm_nl_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(c->pr, c->fm, n_pix, sp, c->D, c->L, K, c->max_degree,
             c->theta, c->nbr, c->obs, c->rows, c->lf_rows, c->nl);
         KLAUNCH(c);
+        }
+        // per candidate row: weight read; per pixel: selected row + ln f, theta, j, ln f cache etc. written
+        KpScope kp(c, BT_KP_MTM_SELECT, (double)M * 4 + n_pix * (2 * D4 + 2 * L4 + D4 + 9));
         mtm_select_kernel<true><<<(n_pix + MTM_WARPS - 1) / MTM_WARPS, MTM_WARPS * 32, 0, c->stream>>>(c->pr, c->fm,
             n_pix, sp, c->D, c->L, K, c->max_degree, c->n_sites > 1, c->theta, c->nbr, c->obs, c->jt, c->rows, c->lf_rows, c->nl,
             seed, t, site, c->gid, usd, uad, c->accept, c->logpa, c->accepted_any);
@@ -777,6 +899,8 @@ extern "C" int bt_mtm_finish(bt_ctx* c, double alpha) {
     gather_rows_kernel<<<(unsigned)(((size_t)n_acc * c->D + 255) / 256), 256, 0, c->stream>>>(c->theta, c->acc_list, n_acc, c->D, c->rows);
     KLAUNCH(c);
     if (run_mlp(c, c->rows, n_acc, c->lf_rows, c->jac_rows)) return -1;
+    const double D4 = 4.0 * c->D, L4 = 4.0 * c->L;
+    KpScope kp(c, BT_KP_MTM_FINISH, n_acc * (4 + L4 + c->fm.T * L4 + 48.0 * c->L + D4 + stencil_bytes(c) + 4 + 2 * D4 + L4 + D4));
     mtm_finish_compact_kernel<<<(n_acc + 127) / 128, 128, 0, c->stream>>>(c->pr, c->fm, n_acc, c->acc_list, c->D, c->L,
         c->max_degree, c->theta, c->nbr, c->obs, c->lf_rows, c->jac_rows, c->nll_lik, c->grad_lik, c->lf_cache, c->v,
         (float)alpha, c->accepted_any);

@@ -907,13 +907,18 @@ static inline int tc3_launch(Tc3Net& t, const FmapDev& fm, const NetDev& net, co
         if (err == cudaSuccess) mlp_tc3_kernel<S_, D_><<<g, TC3_THREADS, t.smem_bytes, stream>>>(t.sched, net, fm, rows, M, lf, jac); \
     } while (0)
     static const int ko = getenv("BT_TC3_KO") ? atoi(getenv("BT_TC3_KO")) : 0;   // compile-time knock-outs (S = 1 only)
+#ifdef BT_KNOCKOUTS     // timing experiments with invalid results: not in the production library (scripts/run_ko.sh builds them)
     if (S == 1 && ko == 4) TC3_LAUNCH(1, 4);
     else if (S == 1 && ko == 8) TC3_LAUNCH(1, 8);
     else if (S == 1 && ko == 256) TC3_LAUNCH(1, 256);
     else if (S == 1 && ko == 268) TC3_LAUNCH(1, 268);
     else if (S == 1 && ko == 260) TC3_LAUNCH(1, 260);
     else if (S == 1 && ko == 1024) TC3_LAUNCH(1, 1024);   // no generic->async proxy fence after the activation stores (results invalid)
-    else if (t.sched.pre_kb > 0) {
+    else
+#else
+    if (ko) return -8;
+#endif
+    if (t.sched.pre_kb > 0) {
         if (t.sched.pre_kb > 3 || !t.sched.pre_img) return -7;
         err = S == 1 ? cudaFuncSetAttribute(mlp_tc3_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes)
                      : cudaFuncSetAttribute(mlp_tc3_kernel<4, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_bytes);

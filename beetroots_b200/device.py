@@ -224,6 +224,12 @@ class DevicePosterior:
             "objective_chromatic": float(oc.sum()), "objective_global": float(og.sum()), "grad": g,
         }
 
+    def get_log_f(self) -> np.ndarray:
+        """ln f(Theta) of the resident state, (N, L), from the per-pixel cache."""
+        log_f = np.empty((self.N, self.L))
+        L.check(self._lib.bt_get_current(self._ctx, L.dptr(log_f), None, None, None, None, None), "bt_get_current")
+        return log_f
+
     def objective_terms(self, owned=None) -> dict:
         """dict_objective of Posterior.compute_all_for_saver (posterior.py:270-330)."""
         out = np.zeros(2 + 2 * self.D)
@@ -414,6 +420,21 @@ class DevicePosterior:
         L.check(self._lib.bt_mlp_profile(self._ctx, int(enable), int(reset), C.byref(ms), C.byref(rows),
                                          C.byref(launches)), "bt_mlp_profile")
         return ms.value, rows.value, launches.value
+
+    KERNEL_PROFILE_NAMES = ("pmala_propose", "pmala_accept", "mtm_gen", "mtm_nl", "mtm_select", "mtm_finish")
+
+    def kernel_profile(self, enable=True, reset=False) -> dict:
+        """Device time (ms), algorithmic HBM bytes and launch count of the memory-bound kernels of the step since the last
+        reset (``bt_kernel_profile``): {name: (ms, bytes, launches)}."""
+        n = len(self.KERNEL_PROFILE_NAMES)
+        ms, by, ln = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int64)
+        L.check(self._lib.bt_kernel_profile(self._ctx, int(enable), int(reset), L.dptr(ms), L.dptr(by), L.dptr(ln, C.c_int64)),
+                "bt_kernel_profile")
+        return {k: (float(ms[i]), float(by[i]), int(ln[i])) for i, k in enumerate(self.KERNEL_PROFILE_NAMES)}
+
+    def reserve_scratch(self, max_rows: int, max_rows_with_jacobian: int = 0):
+        """Allocate the step's scratch buffers up front (``bt_reserve_scratch``): no allocation inside a step afterwards."""
+        L.check(self._lib.bt_reserve_scratch(self._ctx, int(max_rows), int(max_rows_with_jacobian)), "bt_reserve_scratch")
 
     # raw pointer plumbing for halo exchange / e2e bench (device or pinned-host addresses as ints)
     def set_theta_f32_ptr(self, host_ptr: int):

@@ -136,7 +136,11 @@ class ShardedDevicePosterior:
             self.local = DevicePosterior.from_posterior(post_loc, device=device, global_id=self.plan.local_global_id,
                                                         dict_sites=sites, mlp_mode=mlp_mode)
         self.n_sites, self.site_keys = self.local.n_sites, self.local.site_keys
+        self.site_pixels = self.local.site_pixels
         self.dev = torch.device("cuda", device)
+        # tensors handed to the collectives live on the GPU under NCCL; under gloo (several ranks sharing ONE GPU: the
+        # single-device sharding test, tests/test_gpu_parity.py) they are staged through the host
+        self.coll_dev = torch.device("cpu") if (self.world > 1 and dist.get_backend() == "gloo") else self.dev
         self._ids = {}
         if self.world > 1:
             for name in ("send_up", "send_down", "recv_up", "recv_down"):
@@ -155,14 +159,15 @@ class ShardedDevicePosterior:
             t = self._ids[name]
             out = torch.empty((t.numel(), self.D), dtype=torch.float32, device=self.dev)
             self.local.gather_theta_rows(t.data_ptr(), t.numel(), out.data_ptr())
-            return out
+            return out.to(self.coll_dev)                   # (library and torch share the legacy default stream: ordered)
 
         def scatter(name, buf):
             t = self._ids[name]
+            buf = buf.to(self.dev)
             self.local.scatter_theta_rows(t.data_ptr(), t.numel(), buf.data_ptr())
 
         def make_buffer():
-            return torch.empty((self.plan.W, self.D), dtype=torch.float32, device=self.dev)
+            return torch.empty((self.plan.W, self.D), dtype=torch.float32, device=self.coll_dev)
 
         exchange_halo(self.plan, gather, scatter, self.dist, make_buffer)
 
@@ -254,7 +259,10 @@ class ShardedDevicePosterior:
 
     def chain_get(self, first=0, count=None):
         loc = self.local.chain_get(first, count)                         # (T, N_loc, D)
-        return np.swapaxes(self._gather_owned(np.ascontiguousarray(np.swapaxes(loc, 0, 1))), 0, 1) if self.world > 1 else loc
+        if self.world == 1:
+            return loc
+        g = self._gather_owned(np.ascontiguousarray(np.swapaxes(loc, 0, 1)))
+        return None if g is None else np.swapaxes(g, 0, 1)
 
     def chain_stats(self, first=0, count=None, percentiles=(), want_var=False):
         st = self.local.chain_stats(first, count, percentiles, want_var)
@@ -264,18 +272,31 @@ class ShardedDevicePosterior:
             if st[k] is not None:
                 st[k] = self._gather_owned(st[k])
         for k in ("lo", "hi"):
-            st[k] = np.swapaxes(self._gather_owned(np.ascontiguousarray(np.swapaxes(st[k], 0, 1))), 0, 1)
+            g = self._gather_owned(np.ascontiguousarray(np.swapaxes(st[k], 0, 1)))
+            st[k] = None if g is None else np.swapaxes(g, 0, 1)
         return st
 
     def _allreduce(self, arr):
         if self.world == 1:
             return arr
-        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.dev)
+        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.coll_dev)
         self.dist.all_reduce(t)
         return t.cpu().numpy()
 
-    def _gather_owned(self, local_arr):
-        """(N_loc, ...) -> (N, ...) on every rank."""
+    def broadcast_ints(self, values):
+        """The root's integers on every rank (kernel choice, saver decisions, Philox key)."""
+        if self.world == 1:
+            return list(values)
+        t = self.torch.as_tensor(np.asarray(values, dtype=np.int64), device=self.coll_dev)
+        self.dist.broadcast(t, src=0)
+        return [int(x) for x in t.cpu().numpy()]
+
+    def reserve_scratch(self, max_rows, max_rows_with_jacobian=0):
+        self.local.reserve_scratch(max_rows, max_rows_with_jacobian)
+
+    def _gather_owned(self, local_arr, everywhere=False):
+        """(N_loc, ...) -> (N, ...) on the root rank (None elsewhere); on every rank if ``everywhere``.  Only the root
+        talks to the saver, so by default nothing is shipped to, or copied off the device on, the other ranks."""
         if self.world == 1:
             return local_arr
         torch = self.torch
@@ -284,11 +305,20 @@ class ShardedDevicePosterior:
                  for r in range(self.world)]
         # bands may differ by one row: gather equal-sized (zero-padded) pieces and trim, which every backend supports
         smax = max(sizes)
-        mine = torch.zeros((smax,) + tuple(own.shape[1:]), dtype=torch.as_tensor(own).dtype, device=self.dev)
-        mine[:own.shape[0]] = torch.as_tensor(np.ascontiguousarray(own), device=self.dev)
-        outs = [torch.empty_like(mine) for _ in sizes]
-        self.dist.all_gather(outs, mine)
+        mine = torch.zeros((smax,) + tuple(own.shape[1:]), dtype=torch.as_tensor(own).dtype, device=self.coll_dev)
+        mine[:own.shape[0]] = torch.as_tensor(np.ascontiguousarray(own), device=self.coll_dev)
+        if everywhere:
+            outs = [torch.empty_like(mine) for _ in sizes]
+            self.dist.all_gather(outs, mine)
+        else:
+            outs = [torch.empty_like(mine) for _ in sizes] if self.rank == 0 else None
+            self.dist.gather(mine, outs, dst=0)
+            if self.rank != 0:
+                return None
         return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0).cpu().numpy()
+
+    def get_log_f(self):
+        return self._gather_owned(self.local.get_log_f())
 
     def get_state(self, want_v=True, want_j=True):
         th, v, j = self.local.get_state(want_v, want_j)
@@ -308,6 +338,8 @@ class ShardedDevicePosterior:
                 out[k] = self._gather_owned(val)
             else:
                 out[k] = val
+        if self.rank != 0:
+            return {}
         for k in ("objective_chromatic", "objective_global"):
             out[k] = float(out["objective_pix_" + k.split("_")[1]].sum())
         out["nll_utils"] = {"nll": np.float64(out["nll_pix"].sum())}
@@ -325,6 +357,9 @@ class ShardedDevicePosterior:
 
     def model_check_get(self, finalize=True):
         return tuple(self._gather_owned(a) for a in self.local.model_check_get(finalize))
+
+    def kernel_profile(self, enable=True, reset=False):
+        return self.local.kernel_profile(enable, reset)
 
     def synchronize(self):
         self.local.synchronize()

@@ -77,7 +77,8 @@ class B200Sampler:
         self.v = np.zeros((N * D,))
         self.j_t = np.zeros((N * D,))
         self.current = {}
-        self.philox_seed = None
+        self._philox = None                # key of the per-pixel Philox streams of the current sample() call
+        self._user_seed = None             # a key fixed by the caller (tests, benchmarks): ``sampler.philox_seed = k``
         # on-device chain store: keep up to ``device_chain`` post-burn-in iterates (every
         # ``device_chain_thin``-th) in HBM and summarise them there, see posterior_summary()
         assert device_chain >= 0 and device_chain_thin >= 1
@@ -112,6 +113,16 @@ class B200Sampler:
         (sampler/my_sampler.py:103-156 -> csrc/sampler_kernels.cuh mtm_gen_kernel)."""
         raise NotImplementedError("proposals are generated on the device; see DevicePosterior.debug_philox_mtm")
 
+    @property
+    def philox_seed(self):
+        return self._philox
+
+    @philox_seed.setter
+    def philox_seed(self, seed):
+        """Fix the key of the per-pixel Philox streams (None: a fresh one is drawn from ``self.rng`` at every ``sample()``)."""
+        self._user_seed = None if seed is None else int(seed)
+        self._philox = self._user_seed
+
     # ------------------------------------------------------------------ device plumbing
     def attach(self, posterior, dev: Optional[DevicePosterior] = None):
         if dev is not None:
@@ -133,12 +144,32 @@ class B200Sampler:
     def _pull_state(self, with_current=True):
         dev = self._dev
         Theta, v, j = dev.get_state()
+        if Theta is None:                                  # sharded run, not the root rank
+            return
         self.v = v.reshape(-1)
         self.j_t = j.reshape(-1).astype(np.float64)
         if with_current:
             self.current = dev.get_current()
         else:
             self.current = {"Theta": Theta}
+
+    def _pull_for_saver(self, saver, dict_objective):
+        """What the Saver protocol stores of an iterate (sampler/saver/my_saver.py:46-83, 85-144): Theta, v and -- only if the
+        saver keeps forward-map evaluations -- ln f / f.  j, the per-pixel objectives and the gradients stay on the device
+        (the reference recomputes them by ``compute_all_for_saver``; nothing reads them between two iterations)."""
+        dev = self._dev
+        Theta, v, _ = dev.get_state(want_v=True, want_j=False)
+        if Theta is None:                                  # sharded run, not the root rank
+            if getattr(saver, "save_forward_map_evals", True):
+                dev.get_log_f()                            # take part in the gather
+            return False
+        self.v = v.reshape(-1)
+        fm = {}
+        if getattr(saver, "save_forward_map_evals", True):
+            log_f = dev.get_log_f()
+            fm = {"log_f_Theta": log_f, "f_Theta": np.exp(log_f)}
+        self.current = {"Theta": Theta, "forward_map_evals": fm, "nll_utils": {"nll": np.float64(dict_objective["nll"])}}
+        return True
 
     # ------------------------------------------------------------------ kernels
     def generate_new_sample_pmala_rmsprop(self, t: int, posterior, noise: Optional[dict] = None):
@@ -211,15 +242,27 @@ class B200Sampler:
         assert Theta_0 is not None
         assert Theta_0.shape == (self.N, self.D)
         dev = self.attach(posterior)
-        if self.philox_seed is None:
-            self.philox_seed = int(self.rng.integers(0, 2 ** 63 - 1))
+        # Sharded over several GPUs (parallel.ShardedDevicePosterior) every rank runs this loop; only the root talks to the
+        # saver (one writer per results file), the other ranks take part in the collectives behind the pulls.
+        is_root = getattr(dev, "rank", 0) == 0
+        sharded = getattr(dev, "world", 1) > 1
+        # a fresh Philox key per call (a second sample() on the same object continues the host stream like the reference's
+        # rng does); recorded with the results so that a run can be reproduced from its saved state
+        self._philox = int(self.rng.integers(0, 2 ** 63 - 1)) if self._user_seed is None else int(self._user_seed)
+        if sharded:
+            self._philox = int(dev.broadcast_ints([self._philox])[0])
+        if hasattr(dev, "reserve_scratch"):
+            n_max = max([p.size for p in dev.site_pixels] + [1])
+            dev.reserve_scratch(n_max * (self.k_mtm + 1), max(n_max, self.N if not sharded else dev.local.N))
         self.current = dev.compute_all(Theta_0)                                    # :319-323
-        assert np.isnan(self.current["objective_global"]) == 0                    # :325-326
-        assert np.sum(np.isnan(self.current["grad"])) == 0
+        if is_root:
+            assert np.isnan(self.current["objective_global"]) == 0                # :325-326
+            assert np.sum(np.isnan(self.current["grad"])) == 0
         dev.init_v_from_grad()                                                     # :337, :354
-        self.v = self.current["grad"].flatten() ** 2
-        assert np.sum(np.isnan(self.v)) == 0.0
-        assert np.sum(np.isinf(self.v)) == 0.0
+        if is_root:
+            self.v = self.current["grad"].flatten() ** 2
+            assert np.sum(np.isnan(self.v)) == 0.0
+            assert np.sum(np.isinf(self.v)) == 0.0
         self.j_t = np.zeros((self.N * self.D,))
         dev.model_check_reset()                                                    # :385-401
         best_objective = np.inf                                                    # used only if not self.stochastic
@@ -232,7 +275,7 @@ class B200Sampler:
 
         try:
             from tqdm.auto import tqdm
-            it = tqdm(range(1, max_iter + 1), disable=disable_progress_bar)
+            it = tqdm(range(1, max_iter + 1), disable=disable_progress_bar or not is_root)
         except Exception:                                                          # pragma: no cover
             it = range(1, max_iter + 1)
         for t in it:
@@ -245,34 +288,39 @@ class B200Sampler:
                     dev.update_spatial_weights(posterior.prior_spatial, posterior.prior_indicator)
                 additional_sampling_log["tau"] = posterior.prior_spatial.weights * 1
             type_t = int(np.argmax(self.rng.multinomial(1, pvals=self.selection_probas)))   # :430-435
+            # the saver's decisions depend on t and on its own state only, so they are taken before the kernel runs; sharded,
+            # the root's kernel choice and decisions are the ones every rank follows (one small broadcast per iteration)
+            first = is_root and saver.memory == {}
+            need = is_root and (first or saver.check_need_to_update_memory(t))      # :456, :501
+            if sharded:
+                type_t, need = (int(x) for x in dev.broadcast_ints([type_t, int(need)]))
             if type_t == 0:
                 accepted_t, log_proba_accept_t = self.generate_new_sample_mtm(t, posterior)
             else:
                 accepted_t, log_proba_accept_t = self.generate_new_sample_pmala_rmsprop(t, posterior)
 
-            need = (saver.memory == {}) or saver.check_need_to_update_memory(t)      # :456, :501
             if need:
-                first = saver.memory == {}
-                self._pull_state(with_current=True)
-                additional_sampling_log["v"] = self.v.reshape((self.N, self.D)) * 1
-                additional_sampling_log["type_t"] = type_t
-                additional_sampling_log["accepted_t"] = accepted_t
-                additional_sampling_log["log_proba_accept_t"] = log_proba_accept_t
                 dict_objective = dev.objective_terms()                             # posterior.py:270-330
+                have = self._pull_for_saver(saver, dict_objective)
                 if t > T_BI:                                                       # :468-476 / :514-521
                     if self.stochastic:
                         dev.model_check_update(self.philox_seed, t)
                     elif dict_objective["objective"] < best_objective:            # :208-212
                         best_objective = dict_objective["objective"] * 1
                         dev.model_check_snapshot_clppd()
-                kw = dict(Theta=self.current["Theta"], forward_map_evals=self.current["forward_map_evals"],
-                          nll_utils=self.current["nll_utils"], dict_objective=dict_objective,
-                          additional_sampling_log=additional_sampling_log)
-                if first:
-                    saver.initialize_memory(max_iter, t, **kw)                     # :478-486
-                rng_state_array, rng_inc_array = self.get_rng_state()
-                saver.update_memory(t, rng_state_array=rng_state_array, rng_inc_array=rng_inc_array, **kw)
-            if saver.check_need_to_save(t):                                        # :539-541
+                if have:
+                    additional_sampling_log["v"] = self.v.reshape((self.N, self.D)) * 1
+                    additional_sampling_log["type_t"] = type_t
+                    additional_sampling_log["accepted_t"] = accepted_t
+                    additional_sampling_log["log_proba_accept_t"] = log_proba_accept_t
+                    kw = dict(Theta=self.current["Theta"], forward_map_evals=self.current["forward_map_evals"],
+                              nll_utils=self.current["nll_utils"], dict_objective=dict_objective,
+                              additional_sampling_log=additional_sampling_log)
+                    if first:
+                        saver.initialize_memory(max_iter, t, **kw)                 # :478-486
+                    rng_state_array, rng_inc_array = self.get_rng_state()
+                    saver.update_memory(t, rng_state_array=rng_state_array, rng_inc_array=rng_inc_array, **kw)
+            if is_root and saver.check_need_to_save(t):                            # :539-541
                 saver.save_to_file()
             if (self.device_chain and t > T_BI and t % self.device_chain_thin == 0
                     and dev.chain_length() < self.device_chain):
@@ -282,6 +330,7 @@ class B200Sampler:
             for rep in range(self.ESS_OPTIM):
                 dev.model_check_update_pvalues(self.philox_seed, max_iter + 1 + rep)
         clppd, p_values_y, p_values_llh = dev.model_check_get(finalize=True)       # :544-549
-        saver.save_additional(list_arrays=[clppd, p_values_y, p_values_llh],
-                              list_names=["clppd", "p-values-y", "p-values-llh"])   # :551-558
+        if is_root:
+            saver.save_additional(list_arrays=[clppd, p_values_y, p_values_llh, np.array([self.philox_seed], dtype=np.uint64)],
+                                  list_names=["clppd", "p-values-y", "p-values-llh", "philox_seed"])   # :551-558
         return

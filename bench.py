@@ -34,7 +34,8 @@ def parse():
     ap.add_argument("--size", type=int, default=1024, help="map is size x size pixels")
     ap.add_argument("--k-mtm", type=int, default=50)
     ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "bf16"])
-    ap.add_argument("--cpu-size", type=int, default=48, help="side of the bounded CPU-baseline sample map")
+    ap.add_argument("--cpu-size", type=int, default=64, help="side of the bounded CPU-baseline sample map")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K_mtm = 10 / 20 runs and the sample() end-to-end")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -83,10 +84,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(size, k_mtm, steps=1, warmup=0):
-    """The oracle port of the reference step (oracle/sampler.py) timed on the host cores, on a bounded sample:
-    a size x size map, one MTM + one PMALA iteration per step.  Scaled linearly (a LOWER bound on the
-    reference, whose prior loops are O(N*E)) to the 1M-pixel map of the metric."""
+def _port_baseline(size, k_mtm, steps=1, warmup=0):
+    """Fallback when no reference tree is on the box: the float64 numpy oracle port of the step (oracle/sampler.py)."""
     import torch
     from beetroots_b200 import modelling as M
     from beetroots_b200.synthetic import make_problem
@@ -106,7 +105,6 @@ def cpu_baseline(size, k_mtm, steps=1, warmup=0):
         noise = {}
         for s, idx in post.dict_sites.items():
             nb = nbr[idx]
-            # proposals in the spirit of utils.py:274-349 (mean of a random neighbour + N(0, 1/tau))
             pick = nb[np.arange(idx.size), rng.integers(0, 2, idx.size)]
             pick = np.where(pick >= 0, pick, nb[:, 0])
             c = orc.current["Theta"][pick][:, None, :] + rng.standard_normal((idx.size, k_mtm, post.D)) / np.sqrt(
@@ -122,27 +120,63 @@ def cpu_baseline(size, k_mtm, steps=1, warmup=0):
     t0 = time.perf_counter()
     for _ in range(steps):
         one_pair()
-    dt = time.perf_counter() - t0
-    its_small = 2 * steps / dt
+    return (time.perf_counter() - t0) / steps, cores
+
+
+def cpu_baseline(size, k_mtm, pairs=1, warmup=1):
+    """The reference's own CPU implementation of the step on the host cores, on a BOUNDED sample of the workload: a
+    size x size map of the same recipe (D=4, L=10, K_mtm), ``pairs`` x (one MTM + one PMALA iteration) =
+    ``MySampler.generate_new_sample_mtm`` / ``_pmala_rmsprop`` (sampler/my_sampler.py:966-1202, 718-906) of the UNMODIFIED
+    reference package (baseline/_ref, oracle/install_reference.py) run through oracle/refrun.py with every thread pool
+    pinned to all host cores; the numpy oracle port (kind "port") only if no reference tree is on this box.  The c4 figure
+    is the sample's iterations/s scaled LINEARLY by the pixel count -- an upper bound for the reference at 1M pixels, whose
+    prior loops are O(N * edges) (never runnable at c4)."""
+    from oracle import refshim
+    sec = cores = None
+    kind = "port"
+    if refshim.reference_available():
+        try:
+            from oracle import posterior as OP
+            from oracle import refrun
+            from beetroots_b200.synthetic import make_problem
+            cores = refrun.set_host_threads()
+            prob = make_problem(size, size, lambda fm, th: OP.forward_map_compute_all(fm, th, False)["log_f_Theta"], L=10,
+                                k_mtm=k_mtm)
+            if warmup:       # numba JIT + torch warm-up on a tiny map of the same recipe
+                small = make_problem(8, 8, lambda fm, th: OP.forward_map_compute_all(fm, th, False)["log_f_Theta"], L=10,
+                                     k_mtm=k_mtm)
+                refrun.time_reference_kernels(small, pairs=1, warmup=1)
+            sec = refrun.time_reference_kernels(prob, pairs=pairs, warmup=0)
+            kind = "reference"
+        except Exception as e:                    # pragma: no cover - stated in the line
+            sys.stderr.write(f"[bench] reference arm failed ({type(e).__name__}: {e}); timing the oracle port instead\n")
+    if sec is None:
+        sec, cores = _port_baseline(size, k_mtm, steps=pairs, warmup=1 if warmup else 0)
+    its_small = 2.0 / sec
     scaled = its_small * (size * size) / (1024.0 * 1024.0)
-    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{size}x{size} map (K_mtm={k_mtm}, L=10, D=4), {steps} x (1 MTM + 1 PMALA) iterations of the float64 "
-                      f"numpy oracle port in {dt:.1f} s = {its_small:.3f} it/s at {size * size} pixels, scaled linearly "
-                      f"to 1,048,576 pixels (lower bound for the reference: its prior loops are O(N*E))",
-            "seconds": dt}
+    what = ("unmodified reference MySampler kernels (baseline/_ref)" if kind == "reference"
+            else "float64 numpy oracle port (no reference tree on this box)")
+    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{size}x{size} map (K_mtm={k_mtm}, L=10, D=4), {pairs} x (1 MTM + 1 PMALA) iterations of the {what} in "
+                      f"{sec * pairs:.1f} s = {its_small:.4f} it/s at {size * size} pixels; value = that scaled linearly to "
+                      f"1,048,576 pixels (extrapolated: the reference's prior loops are O(N*edges), c4 itself is not runnable)",
+            "its_at_sample_size": its_small, "extrapolated": True, "seconds": sec * pairs}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args.cpu_size, args.k_mtm, steps=max(1, args.steps // 2), warmup=1 if args.warmup else 0)
+    pairs = max(1, min(args.steps // 2, 3))            # bounded: ~9 s per pair at 64 x 64 on 16 cores
+    cb = cpu_baseline(args.cpu_size, args.k_mtm, pairs=pairs, warmup=1 if args.warmup else 0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / cb["value"] if cb["value"] > 0 else None, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"c4: 1024x1024 map, D=4, L=10, K_mtm={args.k_mtm}, p=(0.5,0.5); CPU sample {args.cpu_size}x{args.cpu_size}"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": f"c4: 1024x1024 map, D=4, L=10, K_mtm={args.k_mtm}, p=(0.5,0.5); timed on a bounded "
+                                   f"{args.cpu_size}x{args.cpu_size} sample of the same recipe ({2 * pairs} iterations), "
+                                   f"scaled linearly to 1M pixels", "same_config": False},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "its_at_sample_size", "extrapolated")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -200,37 +234,46 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    n_max = max(p.size for p in sdev.local.site_pixels)
+    sdev.reserve_scratch(n_max * (K + 1), sdev.local.N)        # every scratch buffer of a step exists before anything is timed
+
+    def timed_steps(n_steps, t0_index):
+        """n_steps sampler iterations bracketed by barrier + synchronize: (device ms by CUDA events, max over ranks)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        w0 = time.perf_counter()
+        tt = t0_index
+        for _ in range(n_steps):
+            step(tt)
+            tt += 1
+        e1.record()
+        barrier()
+        wall_ = time.perf_counter() - w0
+        ms_ = e0.elapsed_time(e1)
+        ms_ = max(ms_, wall_ * 1000.0) if ms_ <= 0 else ms_
+        if world > 1:
+            x = torch.tensor([ms_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            ms_ = float(x.item())
+        return ms_, wall_, tt
+
     t = 0
     for _ in range(args.warmup):
         step(t)
         t += 1
     # ---- device-resident timing
     sdev.local.mlp_profile(enable=True, reset=True)
+    sdev.local.kernel_profile(enable=True, reset=True)
     launches0 = sdev.local.kernel_launches()
     clocks = ClockSampler(local)
-    barrier()
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(t)
-        t += 1
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - w0
-    ms = e0.elapsed_time(e1)
+    ms, wall, t = timed_steps(args.steps, t)
     clk = clocks.stop() if rank == 0 else None
     mlp_ms, mlp_rows, mlp_launches = sdev.local.mlp_profile(enable=False, reset=True)
+    kprof = sdev.local.kernel_profile(enable=False, reset=True)
     launches = sdev.local.kernel_launches() - launches0
-    # the library launches on its own stream semantics (legacy default stream): use the wall clock bracketed by
-    # synchronisations as the step time, cross-checked with the events
-    ms = max(ms, wall * 1000.0) if ms <= 0 else ms
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
     value = args.steps / (ms / 1000.0) * (H * W) / (1024.0 * 1024.0)
 
     # ---- end to end: host Theta in, host Theta out, every step (pinned buffers)
@@ -254,6 +297,60 @@ def run_ours(args):
         e2e_s = float(tt.item())
     e2e_val = args.steps / e2e_s * (H * W) / (1024.0 * 1024.0)
 
+    # ---- end to end through the public API: B200Sampler.sample(posterior, saver, ...) with a Saver-protocol saver in
+    # host memory (the reference's call, sampler/my_sampler.py:269-283): state pulled to the host, converted to float64,
+    # handed to the saver every freq_save iterations; model check and objective terms as in the reference loop
+    e2e_sample = None
+    extras = {}
+    if not args.no_extras:
+        from beetroots_b200.saver import ChainSaver
+
+        class DiscardingSaver(ChainSaver):
+            """Full Saver protocol (batches filled in host memory like MySaver's); a finished batch is dropped instead of
+            being appended to a file, so the number measures the sampler's hand-over, not a disk."""
+
+            def save_to_file(self):
+                self.memory = dict()
+
+        e2e_sample = {}
+        n_it = 16
+        for freq in (1, 10):
+            saver = DiscardingSaver(post.N, post.D, post.D, post.L, results_path="", batch_size=2, freq_save=freq,
+                                    save_forward_map_evals=False)
+            smp2 = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N,
+                               rng=np.random.default_rng(43), device=local, mlp_mode=mode)
+            smp2.attach(post, sdev)
+            theta0 = prob.theta_init
+            barrier()
+            w0 = time.perf_counter()
+            smp2.sample(post, saver, n_it, Theta_0=theta0, disable_progress_bar=True, T_BI=0)
+            barrier()
+            dt = time.perf_counter() - w0
+            if world > 1:
+                x = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(x, op=dist.ReduceOp.MAX)
+                dt = float(x.item())
+            e2e_sample[f"freq_save_{freq}"] = {"value": n_it / dt * (H * W) / (1024.0 * 1024.0), "unit": UNIT, "iterations": n_it,
+                                               "seconds": dt}
+        e2e_sample["note"] = ("B200Sampler.sample() incl. the initial compute_all, kernel-type draws, objective terms, model check, "
+                              "float64 hand-over of Theta and v to an in-memory Saver (ChainSaver, save_forward_map_evals=False, "
+                              "batch_size=2) and the final state pull / save_additional")
+        # ---- the reference's own K_mtm values at N >= 64^2 (nn_N64_fixed_angle.yaml:97): device-resident, same timing rules
+        sdev.compute_all(prob.theta_init)
+        sdev.init_v_from_grad()
+        for k_extra in (10, 20):
+            if k_extra == K:
+                continue
+            smp.k_mtm = k_extra
+            for _ in range(2):
+                step(t)
+                t += 1
+            n_e = 6
+            ms_e, _, t = timed_steps(n_e, t)
+            extras[f"k_mtm_{k_extra}"] = {"value": n_e / (ms_e / 1000.0) * (H * W) / (1024.0 * 1024.0), "unit": UNIT, "steps": n_e,
+                                          "warmup": 2, "ms_per_step": ms_e / n_e}
+        smp.k_mtm = K
+
     if rank != 0:
         return
     peaks = {}
@@ -262,17 +359,25 @@ def run_ours(args):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_hbm = peaks.get("hbm_gbs", 6500.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
     achieved = (mlp_rows * flops_row / (mlp_ms / 1000.0)) / 1e12 if mlp_ms > 0 else None
-    traffic = None
-    try:        # DRAM bytes per launch from the committed ncu --set full capture (per forward row x rows per launch)
-        # pre-pass + pair kernel (variant 4, the default) or the pair kernel alone: each has its own committed capture
-        v4 = sdev.local.mlp_kernel_variant() == 4
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01e_forward_map_traffic.json" if v4 else "r01_mlp_tc_traffic.json")))
+    variant = sdev.local.mlp_kernel_variant()
+    traffic, traffic_src = None, None
+    try:        # DRAM bytes per forward row from the committed ncu --set full capture of the same kernels (not measured here)
+        name = {5: "r02_forward_map_traffic.json", 4: "r01e_forward_map_traffic.json"}.get(variant, "r01_mlp_tc_traffic.json")
+        tj = json.load(open(os.path.join(ROOT, "profiles", name)))
         if mode == MLP_BF16_TC and mlp_launches:
             traffic = tj["dram_bytes_per_row"] * mlp_rows / mlp_launches
+            traffic_src = f"static: profiles/{name} (ncu dram__bytes per forward row) x rows per launch of this run"
     except Exception:
         pass
+    hbm = {}
+    for name, (k_ms, k_bytes, k_n) in kprof.items():
+        if k_n and k_ms > 0:
+            gbs = k_bytes / (k_ms / 1000.0) / 1e9
+            hbm[name] = {"achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "kernel_ms": k_ms,
+                         "launches": k_n, "algorithmic_bytes_per_launch": k_bytes / k_n, "share_of_step": k_ms / ms}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -287,16 +392,22 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(n_loc * post.D * 4 + 16)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_flops_per_launch": flops_row * mlp_rows / mlp_launches if mlp_launches else None,
-                     "kernel": "forward-map MLP (pre-pass + pair kernel)" if (mode == MLP_BF16_TC and sdev.local.mlp_kernel_variant() == 4) else "forward-map MLP", "peak_source": peak_src,
+                     "kernel": {5: "forward-map MLP (mlp_pre_mma_kernel + mlp_tc4_kernel)", 4: "forward-map MLP (pre-pass + mlp_tc3 pair kernel)"}.get(variant, "forward-map MLP") if mode == MLP_BF16_TC else "forward-map MLP (mlp_simt_kernel)",
+                     "peak_source": peak_src,
                      "rows": int(mlp_rows), "launches": int(mlp_launches), "kernel_ms": mlp_ms,
                      "share_of_step": mlp_ms / ms if ms > 0 else None,
                      "pixel_candidate_evals_per_s_per_gpu": mlp_rows / (mlp_ms / 1000.0) if mlp_ms > 0 else None},
+        "roofline_hbm": hbm,
     }
+    if e2e_sample is not None:
+        line["e2e_sample"] = e2e_sample
+    if extras:
+        line["extra"] = extras
     if not args.no_cpu_baseline:
-        cb = cpu_baseline(args.cpu_size, K, steps=1, warmup=0)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb = cpu_baseline(args.cpu_size, K, pairs=1, warmup=1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "its_at_sample_size", "extrapolated")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -220,6 +220,21 @@ int64_t bt_kernel_launches(bt_ctx* ctx);
  * number of rows it processed; measured with CUDA events on the context's stream. */
 int bt_mlp_profile(bt_ctx* ctx, int enable, int reset, double* ms, int64_t* rows, int64_t* launches);
 
+/* device time and ALGORITHMIC HBM bytes of the memory-bound kernels of the step (the roofline entries of bench.py next to the
+ * forward map's): arrays of BT_KP_COUNT entries, accumulated since the last call with reset != 0.  Bytes per launch are
+ * counted from the launch shape (per colour pixel / per candidate row figures), not measured. */
+#define BT_KP_PMALA_PROPOSE 0  /* my_sampler.py:752-838: stencil + indicator gradient + preconditioned proposal */
+#define BT_KP_PMALA_ACCEPT 1   /* my_sampler.py:840-903 + likelihood of the candidate (approx_censored_add_mult.py:982-1246) */
+#define BT_KP_MTM_GEN 2        /* utils.py:274-349 */
+#define BT_KP_MTM_NL 3         /* likelihood + priors + proposal density of every candidate row (my_sampler.py:1017-1105) */
+#define BT_KP_MTM_SELECT 4     /* my_sampler.py:1107-1178 */
+#define BT_KP_MTM_FINISH 5     /* my_sampler.py:1182-1197 on the accepted pixels */
+#define BT_KP_COUNT 6
+int bt_kernel_profile(bt_ctx* ctx, int enable, int reset, double* ms, double* bytes, int64_t* launches);
+/* allocate every scratch buffer a step over colour classes of up to max_rows candidate rows needs (candidate rows, their
+ * ln f / Jacobian, the pre-pass hand-over image of the tensor-core forward map), so that no allocation happens inside a step. */
+int bt_reserve_scratch(bt_ctx* ctx, int64_t max_rows, int64_t max_rows_with_jacobian);
+
 #ifdef __cplusplus
 }
 #endif

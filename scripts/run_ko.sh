@@ -1,5 +1,6 @@
 # knock-out timings of the column-major pair kernel (results invalid, timing only)
 mkdir -p gpurun_out
+# (build first, here: BT_NVCC_DEFS=-DBT_KNOCKOUTS python beetroots_b200/build.py --force)
 : > gpurun_out/ko.log
 for f in 0 1 4 8 16 17 21 32 96; do
   BT_TC4_FLAGS=$f timeout 100 python scripts/tc4_time.py 4000000 2>&1 | sed "s/^/flags $f: /" >> gpurun_out/ko.log

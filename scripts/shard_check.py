@@ -18,9 +18,17 @@ out, mode = sys.argv[1], sys.argv[2]
 H, W, K = 37, 24, 6
 world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
+# BT_SHARD_ONE_GPU=1: every rank drives its band on GPU 0 and the collectives go through gloo on the host -- the same
+# make_band_plan / exchange_halo / reduction code as over NCCL, testable on a single-GPU machine
+ONE_GPU = os.environ.get("BT_SHARD_ONE_GPU") == "1"
+if ONE_GPU:
+    local = 0
 torch.cuda.set_device(local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if ONE_GPU:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 mlp = MLP_BF16_TC if mode == "bf16" else MLP_FP32
 NEXT = mode == "next"          # fp32 + the "next" rows: chain store, optimisation mode, regularisation-weight update
 prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K, use_next_nearest_neighbors=(mode == "fp32n8"))

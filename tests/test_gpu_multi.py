@@ -10,15 +10,46 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, out, mode):
+def _run(world, out, mode, one_gpu=False):
     script = os.path.join(ROOT, "scripts", "shard_check.py")
+    env = dict(os.environ)
+    if one_gpu:
+        env["BT_SHARD_ONE_GPU"] = "1"
     if world == 1:
         cmd = [sys.executable, script, out, mode]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", script, out, mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _compare(a, b, mode, what):
+    for k in ("theta", "v", "j"):
+        assert np.array_equal(a[k], b[k]), f"{k} differs between 1 and {what} ({mode})"
+    assert np.allclose(a["stats"], b["stats"], rtol=1e-12, atol=1e-12)
+    assert np.isclose(a["objective"], b["objective"], rtol=1e-9)
+    if mode == "next":
+        # chain store and its summaries: per-pixel work, bit-identical; optimisation mode: the global argmin / objective
+        # comparison go through an all-reduce (same decisions, same states); after the regularisation-weight update the
+        # weights agree to double rounding of the reduced potential, the states to float32 rounding of those weights
+        for k in ("chain", "chain_mean", "chain_var", "chain_lo", "chain_hi", "theta_opt"):
+            assert np.array_equal(a[k], b[k]), f"{k} differs between 1 and {what}"
+        assert np.array_equal(a["opt_stats"], b["opt_stats"]) and np.isclose(a["opt_objective"], b["opt_objective"], rtol=1e-9)
+        assert np.allclose(a["taus"], b["taus"], rtol=1e-10) and np.abs(a["taus"][-1] - a["taus"][0]).max() > 0
+        assert np.allclose(a["theta_tau"], b["theta_tau"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "next"])
+def test_sharded_chain_on_one_gpu_is_bit_identical(tmp_path, built_lib, mode):
+    """Runs on a single-GPU machine: 3 ranks share GPU 0, each owns a row band (own context, ghost rows), the halo
+    exchange and the global reductions go through gloo on the host -- the band plan, exchange and reduction code is the one
+    used over NCCL.  The sharded chain must be the unsharded chain bit for bit."""
+    ref = str(tmp_path / "w1.npz")
+    _run(1, ref, mode)
+    out = str(tmp_path / "w3.npz")
+    _run(3, out, mode, one_gpu=True)
+    _compare(np.load(ref), np.load(out), mode, "3 bands on one GPU")
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp32n8", "bf16", "next"])
@@ -33,17 +64,4 @@ def test_sharded_chain_is_bit_identical(tmp_path, built_lib, mode):
     for world in [w for w in (2, 3, 4, 8) if w <= n][:2]:
         out = str(tmp_path / f"w{world}.npz")
         _run(world, out, mode)
-        b = np.load(out)
-        for k in ("theta", "v", "j"):
-            assert np.array_equal(a[k], b[k]), f"{k} differs between 1 and {world} GPUs ({mode})"
-        assert np.allclose(a["stats"], b["stats"], rtol=1e-12, atol=1e-12)
-        assert np.isclose(a["objective"], b["objective"], rtol=1e-9)
-        if mode == "next":
-            # chain store and its summaries: per-pixel work, bit-identical; optimisation mode: the global argmin / objective
-            # comparison go through an all-reduce (same decisions, same states); after the regularisation-weight update the
-            # weights agree to double rounding of the reduced potential, the states to float32 rounding of those weights
-            for k in ("chain", "chain_mean", "chain_var", "chain_lo", "chain_hi", "theta_opt"):
-                assert np.array_equal(a[k], b[k]), f"{k} differs between 1 and {world} GPUs"
-            assert np.array_equal(a["opt_stats"], b["opt_stats"]) and np.isclose(a["opt_objective"], b["opt_objective"], rtol=1e-9)
-            assert np.allclose(a["taus"], b["taus"], rtol=1e-10) and np.abs(a["taus"][-1] - a["taus"][0]).max() > 0
-            assert np.allclose(a["theta_tau"], b["theta_tau"], rtol=1e-5, atol=1e-6)
+        _compare(a, np.load(out), mode, f"{world} GPUs")

@@ -131,6 +131,7 @@ class _RecordingDevice:
     def get_state(self, want_v=True, want_j=True):
         return self.theta.copy(), np.ones((self.N, self.D)), np.zeros((self.N, self.D), dtype=np.int32)
 
+    def get_log_f(self): return np.zeros((self.N, self.L))
     def init_v_from_grad(self): self._rec("init_v")
     def model_check_reset(self): self._rec("mc_reset")
     def begin_iteration(self): self._rec("begin")
@@ -210,7 +211,7 @@ def test_sample_control_flow_regu_weights_and_device_chain():
             assert kinds[i + 1] == "weights" and kinds[i + 2] == "begin"
     assert ("chain_reserve", 3) in dev.calls and len(dev.chain) == 3         # t = 4, 6, 8 (t > T_BI, even), then full
     assert [c[1] for c in dev.calls if c[0] == "mc_update"] == list(range(4, 11))   # model check only after burn-in
-    assert sv.additional == ["clppd", "p-values-y", "p-values-llh"]
+    assert sv.additional == ["clppd", "p-values-y", "p-values-llh", "philox_seed"]
 
 
 def test_sample_control_flow_optimisation_mode():

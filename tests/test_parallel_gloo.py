@@ -128,6 +128,7 @@ def _reduction_worker(rank, world, port, H, W, out_dir):
     nbl = M.build_neighbor_table(lp.prior_spatial.list_edges, plan.n_local, 4)
     sh = object.__new__(ShardedDevicePosterior)                      # the host logic without a CUDA context
     sh.torch, sh.dist, sh.world, sh.rank, sh.plan, sh.dev = torch, dist, world, rank, plan, torch.device("cpu")
+    sh.coll_dev = sh.dev
     sh.N, sh.D, sh.L = N, D, L
     th_loc = theta[gid]
     ok = True
@@ -145,14 +146,23 @@ def _reduction_worker(rank, world, port, H, W, out_dir):
         col = (sp.weights * had_g).sum(-1).sum(axis=0)
         red = sh._allreduce(col_loc)
         ok &= bool(np.allclose(red, col, rtol=1e-12)) and int(np.argmin(red)) == int(np.argmin(col))
-    # (3) per-pixel arrays and the stored chain come back in global pixel order
-    ok &= bool(np.array_equal(sh._gather_owned(th_loc), theta))
+    # (3) per-pixel arrays and the stored chain come back in global pixel order: on the root by default (the only rank that
+    # talks to the saver), on every rank on request
+    def G(a):
+        g0, g = sh._gather_owned(a), sh._gather_owned(a, everywhere=True)
+        assert (g0 is None) == (rank != 0)
+        assert g0 is None or (g0.dtype == g.dtype and np.array_equal(g0, g))
+        return g
+
+    ok &= bool(np.array_equal(G(th_loc), theta))
     jj = np.arange(N * D, dtype=np.int32).reshape(N, D)                      # the RMSProp counters travel as int32
-    got = sh._gather_owned(jj[gid])
+    got = G(jj[gid])
     ok &= got.dtype == np.int32 and bool(np.array_equal(got, jj))
-    ok &= bool(np.array_equal(sh._gather_owned(theta[gid, 0]), theta[:, 0]))   # 1-D per-pixel arrays (objectives, accept)
-    ch = np.swapaxes(sh._gather_owned(np.ascontiguousarray(np.swapaxes(chain[:, gid], 0, 1))), 0, 1)
+    ok &= bool(np.array_equal(G(theta[gid, 0]), theta[:, 0]))                # 1-D per-pixel arrays (objectives, accept)
+    ch = np.swapaxes(G(np.ascontiguousarray(np.swapaxes(chain[:, gid], 0, 1))), 0, 1)
     ok &= bool(np.array_equal(ch, chain))
+    # (4) the root's kernel choice / saver decisions / Philox key reach every rank
+    ok &= sh.broadcast_ints([rank * 7 + 3, 2 ** 62 + rank]) == [3, 2 ** 62]
     np.save(os.path.join(out_dir, f"red{rank}.npy"), np.array([ok]))
     dist.destroy_process_group()
 
@@ -163,3 +173,89 @@ def test_global_reductions_of_the_next_rows_gloo(tmp_path, world):
     mp.spawn(_reduction_worker, args=(world, port, 9, 5, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert np.load(tmp_path / f"red{r}.npy")[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sample() on several ranks: one writer, the root's decisions everywhere
+class _ShardedStandIn:
+    """The surface of parallel.ShardedDevicePosterior that B200Sampler.sample uses, without a GPU: per-pixel arrays exist
+    on the root only (the other ranks get None, as from _gather_owned), scalars are the same everywhere, broadcast_ints goes
+    through the process group."""
+
+    def __init__(self, N, D, L, rank, world):
+        self.N, self.D, self.L, self.rank, self.world = N, D, L, rank, world
+        self.n_sites, self.site_keys = 2, [0, 1]
+        self.kinds, self.theta = [], np.zeros((N, D))
+
+    def broadcast_ints(self, values):
+        t = torch.as_tensor(np.asarray(values, dtype=np.int64))
+        dist.broadcast(t, src=0)
+        return [int(x) for x in t.numpy()]
+
+    def _root(self, a):
+        return a if self.rank == 0 else None
+
+    def compute_all(self, Theta=None):
+        N, D = self.N, self.D
+        return {"Theta": self.theta, "objective_global": 1.0, "grad": np.ones((N, D))} if self.rank == 0 else {}
+
+    def get_current(self, with_forward_map=True):
+        return self.compute_all()
+
+    def get_state(self, want_v=True, want_j=True):
+        return (self._root(self.theta.copy()), self._root(np.ones((self.N, self.D))),
+                self._root(np.zeros((self.N, self.D), dtype=np.int32)))
+
+    def get_log_f(self): return self._root(np.zeros((self.N, self.L)))
+    def init_v_from_grad(self): pass
+    def model_check_reset(self): pass
+    def begin_iteration(self): pass
+    def pmala_site(self, s, *a): self.kinds.append(1); self.theta += 0.25
+    def mtm_site(self, s, *a): self.kinds.append(0); self.theta += 0.5
+    def mtm_finish(self, alpha): pass
+    def reduce_step_stats(self): return np.array([self.N / 2.0, -3.0 * self.N])
+    def model_check_update(self, seed, t, *a): self.kinds.append(("mc", seed))
+    def model_check_get(self, finalize=True):
+        return self._root(np.zeros((self.N, self.L))), self._root(np.zeros((self.N, self.L))), self._root(np.zeros(self.N))
+    def objective_terms(self):
+        return {"nll": np.float64(2.0), "nl_prior_spatial": np.zeros(self.D), "nl_prior_indicator": np.zeros(self.D),
+                "objective": np.float64(2.0)}
+
+
+def _sample_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from beetroots_b200 import B200Sampler, MySamplerParams
+    from beetroots_b200.saver import ChainSaver
+    N, D, L, T = 6, 4, 3, 8
+    X, Y = np.repeat(np.arange(N // 2), 2), np.tile(np.arange(2), N // 2)
+    post = M.Posterior(D, L, N, M.MixingModelsLikelihood(None, D, L, N, np.ones((N, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)),
+                                                         a1=np.ones((1, L))),
+                       M.L22DiscreteGradSpatialPrior(D, N, X, Y, None, False, np.ones(D)),
+                       M.SmoothIndicatorPrior(D, N, 0.1, -np.ones(D), np.ones(D)))
+    dev = _ShardedStandIn(N, D, L, rank, world)
+    # every rank seeds its host generator DIFFERENTLY: kernel choice and Philox key must still be the root's
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], 3, True, False), D, L, N, rng=np.random.default_rng(100 + rank))
+    smp.attach(post, dev)
+    saver = ChainSaver(N, D, D, L, results_path=os.path.join(out_dir, "results"), batch_size=2, freq_save=2)
+    smp.sample(post, saver, T, Theta_0=np.zeros((N, D)), disable_progress_bar=True, T_BI=2)
+    np.save(os.path.join(out_dir, f"kinds{rank}.npy"), np.array([k if isinstance(k, int) else -1 for k in dev.kinds]))
+    np.save(os.path.join(out_dir, f"seed{rank}.npy"), np.array([smp.philox_seed] + [k[1] for k in dev.kinds if not isinstance(k, int)]))
+    np.save(os.path.join(out_dir, f"wrote{rank}.npy"), np.array([len(saver.saved), len(saver.memory)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sample_on_several_ranks_has_one_writer(tmp_path, world):
+    """B200Sampler.sample over a sharded device: only the root initialises / updates / saves (one results file, no
+    concurrent writers), every rank runs the kernels the ROOT drew with the ROOT's Philox key and takes the same saver
+    branches (identical call sequences: no deadlock in the collectives behind them)."""
+    port = _free_port()
+    mp.spawn(_sample_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    k0 = np.load(tmp_path / "kinds0.npy")
+    for r in range(1, world):
+        assert np.array_equal(np.load(tmp_path / f"kinds{r}.npy"), k0)
+        assert np.array_equal(np.load(tmp_path / f"seed{r}.npy"), np.load(tmp_path / "seed0.npy"))
+        assert np.array_equal(np.load(tmp_path / f"wrote{r}.npy"), [0, 0])       # never touched its saver
+    assert np.load(tmp_path / "wrote0.npy")[0] > 0
+    assert len([f for f in os.listdir(tmp_path / "results") if f.startswith("mc_chains")]) == 1
