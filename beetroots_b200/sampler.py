@@ -67,9 +67,15 @@ class B200Sampler:
         self.stochastic = p.is_stochastic
         self.compute_correction_term = p.compute_correction_term
         if self.compute_correction_term:
-            raise NotImplementedError("the PMALA correction term needs the Hessian diagonal, which the reference "
-                                      "itself cannot evaluate with a spatial prior (posterior.py:259); "
-                                      "use compute_correction_term=False")
+            # NOT BUILT (second half): the bias-correction term of the preconditioned proposal needs the
+            # diagonal of the Hessian of the negative log-posterior (my_sampler.py:771-793, 828-840) -- a second-order
+            # forward-mode pass through the network (neural_network_approx.py:237-265) and the reference's hess_diag formulas
+            # (approx_censored_add_mult.py:745-980).  In the reference it only runs WITHOUT a spatial prior (posterior.py:259
+            # calls prior_spatial.hess_diag_neglog_pdf without idx_pix).  MySamplerParams defaults to True like the
+            # reference's, so a drop-in caller must pass compute_correction_term=False explicitly.
+            raise NotImplementedError("B200Sampler does not implement the Hessian-diagonal correction term of PMALA "
+                                      "(compute_correction_term=True); construct MySamplerParams(..., "
+                                      "compute_correction_term=False)")
         self.D, self.L, self.N = D, L, N
         self.rng = np.random.default_rng(42) if rng is None else rng
         self.device = device

@@ -313,7 +313,7 @@ def run_ours(args):
                 self.memory = dict()
 
         e2e_sample = {}
-        n_it = 16
+        n_it = 20            # (a multiple of both freq_save values: MySaver sizes its last batch (T_MC - t + 1) // freq_save)
         for freq in (1, 10):
             saver = DiscardingSaver(post.N, post.D, post.D, post.L, results_path="", batch_size=2, freq_save=freq,
                                     save_forward_map_evals=False)

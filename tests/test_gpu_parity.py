@@ -77,7 +77,7 @@ def test_steps_vs_reference_golden(lib, name):
     dev.close()
 
 
-BF16_FLIP_BUDGET = 0.10      # stated: at most 10 % of the per-pixel outcomes of a step may differ from the reference tape
+BF16_FLIP_BUDGET = 0.03      # stated: at most 3 % of the per-pixel outcomes of the tape may differ (observed: 0 / 180 and 1 / 140)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -87,7 +87,7 @@ def test_bf16_steps_vs_reference_golden(lib, name):
     The bf16 emulator differs from the float64 one by |d ln f| <= 3e-2 (rms 2e-3, i.e. 2 % of sigma_m per line), which moves a
     log acceptance ratio by ~0.1 nat: a decision flips when log u falls in that window.  Trajectories diverge after a flip,
     so every step starts from the REFERENCE state of the tape (Theta, v, j of t - 1) and is compared with the reference
-    state of t.  Stated bounds: (a) at most BF16_FLIP_BUDGET of the per-pixel outcomes of a step (accept / reject, and for
+    state of t.  Stated bounds: (a) at most BF16_FLIP_BUDGET of the per-pixel outcomes (2 per step) (accept / reject, and for
     MTM the selected candidate) differ; (b) where the outcome is the same, |log ratio - reference| <= 0.35 + 5 % and the new
     state agrees to 2 % of the move + 1e-4 (PMALA: the drift uses the bf16 Jacobian; MTM: the state is one of the tape's
     candidates, hence exact)."""
@@ -284,7 +284,7 @@ def test_sample_runs_with_saver_protocol(lib):
     assert len(sv.saved) == 2 and sum(len(m["list_Theta"]) for m in sv.saved) == 10
     objs = np.concatenate([m["list_objective"] for m in sv.saved])
     assert np.all(np.isfinite(objs))
-    assert set(sv.additional) == {"clppd", "p-values-y", "p-values-llh"}
+    assert set(sv.additional) == {"clppd", "p-values-y", "p-values-llh", "philox_seed"}
     assert smp.current["Theta"].shape == (post.N, post.D) and np.all(np.isfinite(smp.v))
 
 
