@@ -8,6 +8,10 @@ from beetroots_b200.network import synthetic_weights
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["ref_n4_6x5", "ref_n8_5x6_censored"]
+# BASELINE-sized tapes of the unmodified reference (make_golden.py --big): c2 = 30x30, K=50, 6 iterations; c3-like = 64x64,
+# 29 % censored, K=10, step size 1e-2 (16-18 % of the moves rejected), 5 iterations.  Compact storage: float32 noise (exactly
+# what the reference consumed), float32 v / grad.
+GOLDEN_BIG = ["ref_c2_30x30", "ref_c3_64x64_censored"]
 
 
 def load_golden(name):

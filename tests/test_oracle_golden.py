@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from _cases import GOLDEN, GOLDEN_CASES, golden_noise, load_golden, problem_from_golden
+from _cases import GOLDEN, GOLDEN_BIG, GOLDEN_CASES, golden_noise, load_golden, problem_from_golden
 from oracle import posterior as OP
 from oracle.sampler import OracleSampler
 
@@ -175,3 +175,25 @@ def test_optimisation_mode_matches_reference(name):
         assert rel(orc.current["Theta"], go[f"t{t}_Theta"]) < 1e-9
         assert rel(orc.v, go[f"t{t}_v"]) < 1e-8
         assert abs(orc.current["objective_global"] - float(go[f"t{t}_objective"])) < 1e-8 * abs(float(go[f"t{t}_objective"]))
+
+
+@pytest.mark.parametrize("name", GOLDEN_BIG)
+def test_oracle_follows_the_baseline_sized_reference_tapes(name):
+    """c2 (30x30, K=50) and the c3-like 64x64 censored map: the oracle replays the tape of the unmodified reference with identical
+    accept / reject decisions at every pixel and iteration (thousands of decisions, 16-18 % rejections in the c3 case)."""
+    g = load_golden(name)
+    post, nbr = problem_from_golden(g)
+    orc = OracleSampler(post, nbr, float(g["eps"]), 1e-5, 0.99, int(g["K"]))
+    orc.init(g["theta0"])
+    assert rel(orc.current["objective_pix_chromatic"], g["init_obj_chrom"]) < 1e-9
+    n_rej = 0
+    for t, kind in enumerate(g["kernels"], start=1):
+        noise = golden_noise(g, t, int(kind), post)
+        noise = {s: {k: np.asarray(v, dtype=np.float64) for k, v in d.items()} for s, d in noise.items()}
+        acc, lpa = orc.pmala_step(noise) if kind == 1 else orc.mtm_step(noise)
+        assert np.array_equal(acc > 0, g[f"t{t}_accept"] > 0), f"{name}: decisions differ at t={t}"
+        n_rej += int((acc == 0).sum())
+        assert rel(orc.current["Theta"], g[f"t{t}_Theta"]) < 1e-9
+        assert np.allclose(orc.v, g[f"t{t}_v"], rtol=2e-6)                 # stored as float32
+        assert np.array_equal(orc.j_t, g[f"t{t}_j"])
+    assert n_rej > 0.02 * len(g["kernels"]) * post.N
