@@ -150,21 +150,22 @@ class B200Sampler:
     def _pull_state(self, with_current=True):
         dev = self._dev
         Theta, v, j = dev.get_state()
+        cur = dev.get_current() if with_current else None      # (sharded: every rank takes part in the gathers)
         if Theta is None:                                  # sharded run, not the root rank
             return
         self.v = v.reshape(-1)
         self.j_t = j.reshape(-1).astype(np.float64)
-        if with_current:
-            self.current = dev.get_current()
-        else:
-            self.current = {"Theta": Theta}
+        self.current = cur if with_current else {"Theta": Theta}
 
     def _pull_for_saver(self, saver, dict_objective):
         """What the Saver protocol stores of an iterate (sampler/saver/my_saver.py:46-83, 85-144): Theta, v and -- only if the
         saver keeps forward-map evaluations -- ln f / f.  j, the per-pixel objectives and the gradients stay on the device
         (the reference recomputes them by ``compute_all_for_saver``; nothing reads them between two iterations)."""
         dev = self._dev
-        Theta, v, _ = dev.get_state(want_v=True, want_j=False)
+        try:
+            Theta, v, _ = dev.get_state(want_v=True, want_j=False, reuse=True)     # (host buffers reused: the saver copies)
+        except TypeError:                                  # sharded / stand-in devices without the option
+            Theta, v, _ = dev.get_state(want_v=True, want_j=False)
         if Theta is None:                                  # sharded run, not the root rank
             if getattr(saver, "save_forward_map_evals", True):
                 dev.get_log_f()                            # take part in the gather
@@ -228,6 +229,8 @@ class B200Sampler:
         assert self._dev is not None and self.device_chain, "no chain was kept on the device"
         per = sorted({(100 - ci) / 2 for ci in list_CI} | {100 - (100 - ci) / 2 for ci in list_CI})
         st = self._dev.chain_stats(first, count, per)
+        if st["mean"] is None:                             # sharded run, not the root rank (it took part in the gathers)
+            return {}
         f = (lambda a: a) if from_scaled_to_lin is None else (lambda a: from_scaled_to_lin(a.reshape(-1, self.D)).reshape(a.shape))
         out = {"Theta_MMSE_scaled": st["mean"], "Theta_MMSE": f(st["mean"]), "count": st["count"]}
         for q, p in enumerate(per):
@@ -315,7 +318,7 @@ class B200Sampler:
                         best_objective = dict_objective["objective"] * 1
                         dev.model_check_snapshot_clppd()
                 if have:
-                    additional_sampling_log["v"] = self.v.reshape((self.N, self.D)) * 1
+                    additional_sampling_log["v"] = self.v.reshape((self.N, self.D))     # (the saver copies it into its batch)
                     additional_sampling_log["type_t"] = type_t
                     additional_sampling_log["accepted_t"] = accepted_t
                     additional_sampling_log["log_proba_accept_t"] = log_proba_accept_t

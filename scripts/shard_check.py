@@ -29,7 +29,7 @@ if world > 1:
         dist.init_process_group("gloo")
     else:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-mlp = MLP_BF16_TC if mode == "bf16" else MLP_FP32
+mlp = MLP_BF16_TC if mode in ("bf16", "samplebf16") else MLP_FP32
 NEXT = mode == "next"          # fp32 + the "next" rows: chain store, optimisation mode, regularisation-weight update
 prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K, use_next_nearest_neighbors=(mode == "fp32n8"))
 post = prob.posterior
@@ -73,6 +73,24 @@ if NEXT:
         taus.append(tau_t)
         smp.generate_new_sample_mtm(t, post) if t % 2 == 0 else smp.generate_new_sample_pmala_rmsprop(t, post)
     extra.update(taus=np.array(taus), theta_tau=sdev.get_state()[0])
+if mode in ("sample", "samplebf16"):
+    # the public entry point on the sharded device: B200Sampler.sample with a Saver (only the root writes), regularisation
+    # weights updated from iteration 3 on, on-device chain store; every rank seeds its host generator differently
+    from beetroots_b200.saver import ChainSaver
+    rank = int(os.environ.get("RANK", "0"))
+    smp2 = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N, device=local,
+                       mlp_mode=mlp, rng=np.random.default_rng(5 if rank == 0 else 1000 + rank), device_chain=3, device_chain_thin=2)
+    smp2.attach(post, sdev)
+    sv = ChainSaver(post.N, post.D, post.D, post.L, results_path="", batch_size=4, freq_save=2, save_forward_map_evals=True)
+    smp2.sample(post, sv, 8, Theta_0=prob.theta_init, disable_progress_bar=True, regu_spatial_N0=3, T_BI=2)
+    summ = smp2.posterior_summary(list_CI=(68,))
+    if rank == 0:
+        extra.update(s_theta=sv.saved["list_Theta"], s_v=sv.saved["list_v"], s_logf=sv.saved["list_log_f_Theta"],
+                     s_obj=sv.saved["list_objective"], s_type=sv.saved["list_type_t"], s_acc=sv.saved["list_accepted_t"],
+                     s_tau=sv.saved["list_tau"], s_clppd=sv.saved["clppd"], s_seed=sv.saved["philox_seed"],
+                     s_mmse=summ["Theta_MMSE"], s_final=smp2.current["Theta"])
+    else:
+        assert sv.saved == {} and sv.memory == {}, "only the root may touch the saver"
 if int(os.environ.get("RANK", "0")) == 0:
     np.savez(out, theta=th, v=v, j=j, stats=np.array(stats), objective=terms["objective"], **extra)
     print("world", world, "accept/logpa per iteration", np.array(stats).round(4).tolist(), "objective", terms["objective"])
