@@ -196,9 +196,23 @@ def run_ours(args):
     assert world == args.gpus or world == 1, (world, args.gpus)
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries the ONE JSON line and nothing else: NCCL's own banner (NCCL_DEBUG=VERSION/INFO) goes to stderr
+        # stdout carries the ONE JSON line and nothing else: NCCL prints its banner (NCCL_DEBUG=VERSION/INFO) on fd 1 when the
+        # first communicator is created, so fd 1 points at stderr until that has happened
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            dist.broadcast(warm, src=0)
+            dist.gather(warm, [torch.zeros(1, device="cuda") for _ in range(world)] if rank == 0 else None, dst=0)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     H = W = args.size
     K = args.k_mtm
     mode = {"fp32": MLP_FP32, "bf16": MLP_BF16_TC}.get(args.mlp)
