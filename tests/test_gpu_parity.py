@@ -527,6 +527,72 @@ def test_posterior_statistics_vs_oracle(lib, mode):
     assert 0.75 < wg / width(o) < 1.33
 
 
+def _ess(chain):
+    """Effective sample size per series of a chain (T, ...), Gelman et al. BDA3 as in the reference's
+    inversion/results/utils/mc_utils/ess.py:12-90 for one chain: rho_t from the autocovariance (the variogram form of the
+    reference is the same estimator up to end effects), summed until the first even t where rho_{t-1} + rho_t < 0."""
+    T = chain.shape[0]
+    x = chain.reshape(T, -1) - chain.reshape(T, -1).mean(axis=0)
+    n_fft = 1 << int(np.ceil(np.log2(2 * T)))
+    f = np.fft.rfft(x, n=n_fft, axis=0)
+    acov = np.fft.irfft(f * np.conj(f), n=n_fft, axis=0)[:T] / (T - np.arange(T))[:, None]
+    rho = acov / np.maximum(acov[0], 1e-300)
+    n_pairs = (T - 1) // 2
+    pair = rho[1:2 * n_pairs + 1:2] + rho[2:2 * n_pairs + 2:2]            # rho_{2k-1} + rho_{2k}
+    neg = pair < 0
+    first = np.where(neg.any(axis=0), neg.argmax(axis=0), n_pairs)        # pairs kept before the first negative one
+    keep = np.arange(n_pairs)[:, None] < first[None, :]
+    tau = 1.0 + 2.0 * (pair * keep).sum(axis=0)
+    return (T / np.maximum(tau, 1.0)).reshape(chain.shape[1:])
+
+
+def test_c2_posterior_bf16_vs_fp32_within_ess_error(lib):
+    """Config c2 (30x30, D=4, L=10, K=50): posterior means of the bf16 tensor-core chain against the float32 chain (the path
+    that follows the reference's tapes decision by decision) with an ESS-based Monte-Carlo error: z = difference of the means
+    over sqrt(sd_a^2 / ESS_a + sd_b^2 / ESS_b) per (pixel, parameter).  Two float32 chains with different Philox keys calibrate
+    the yardstick (their z must look standard normal); the bf16-vs-float32 z must look the same: median |z| < 1, at most 3 %
+    beyond 3, and 68 % interval widths within 15 % (median over the map)."""
+    from beetroots_b200 import MLP_BF16_TC, MLP_FP32, B200Sampler, DevicePosterior, MySamplerParams
+    H = W = 30
+    K, T, T_BI, eps = 50, 2400, 400, 3e-3
+    prob = _synthetic(H, W, K)
+    post = prob.posterior
+    N, D = post.N, post.D
+    kinds = np.random.default_rng(6).integers(0, 2, size=T)
+
+    def gpu_chain(seed, mlp):
+        dev = DevicePosterior.from_posterior(post, mlp_mode=mlp)
+        dev.compute_all(prob.theta_init)
+        dev.init_v_from_grad()
+        smp = B200Sampler(MySamplerParams(eps, 1e-5, 0.99, [0.5, 0.5], K, True, False), D, post.L, N, mlp_mode=mlp)
+        smp.attach(post, dev)
+        smp.philox_seed = seed
+        chain = np.zeros((T - T_BI, N, D))
+        for t in range(T):
+            if kinds[t] == 0:
+                smp.generate_new_sample_mtm(t + 1, post)
+            else:
+                smp.generate_new_sample_pmala_rmsprop(t + 1, post)
+            if t >= T_BI:
+                chain[t - T_BI] = dev.get_state(False, False)[0]
+        dev.close()
+        return chain
+
+    a, b, c = gpu_chain(11, MLP_FP32), gpu_chain(22, MLP_FP32), gpu_chain(33, MLP_BF16_TC)
+    stats = [(x.mean(0), x.var(0, ddof=1) / _ess(x)) for x in (a, b, c)]
+    z_ab = (stats[0][0] - stats[1][0]) / np.sqrt(stats[0][1] + stats[1][1])
+    z_ac = (stats[0][0] - stats[2][0]) / np.sqrt(stats[0][1] + stats[2][1])
+    ess_med = float(np.median(_ess(a)))
+    print(f"[c2 posterior] ESS median {ess_med:.0f} of {T - T_BI}; |z| fp32-vs-fp32: median {np.median(np.abs(z_ab)):.2f}, "
+          f">3: {np.mean(np.abs(z_ab) > 3):.4f}; bf16-vs-fp32: median {np.median(np.abs(z_ac)):.2f}, >3: {np.mean(np.abs(z_ac) > 3):.4f}")
+    assert ess_med > 20, "chains too short for the statement"
+    assert np.median(np.abs(z_ab)) < 1.0 and np.mean(np.abs(z_ab) > 3) < 0.03, "the yardstick itself is off"
+    assert np.median(np.abs(z_ac)) < 1.0 and np.mean(np.abs(z_ac) > 3) < 0.03, "bf16 posterior means differ beyond Monte-Carlo error"
+    width = lambda x: np.percentile(x, 84, axis=0) - np.percentile(x, 16, axis=0)      # noqa: E731
+    wa, wc = width(a), width(c)
+    assert np.median(np.abs(wa - wc) / (0.5 * (wa + wc))) < 0.15
+
+
 def test_tensor_core_variants_agree(lib):
     """The three tensor-core kernels against each other.  The first cta_group::2 kernel (BT_TC_VARIANT=2) must return
     exactly what the single-CTA kernel (1) returns: same bf16 operands, same accumulation order per column.  The default
