@@ -75,6 +75,26 @@ class MixingModelsLikelihood:
         return np.ascontiguousarray(v)
 
 
+def saver_nll_utils(likelihood, log_f: np.ndarray) -> dict:
+    """The per-(pixel, line) entries of ``nll_utils`` that the reference saver stores next to the chain
+    (sampler/saver/my_saver.py:57-61, 128-130: every key without ``nll_`` / ``grad`` / ``hess_diag``), evaluated on the host in
+    float64 from ln f of the saved iterate -- saver glue, NOT the hot path (the device fuses these quantities into the
+    likelihood kernels and never stores them).  Formulas: likelihoods/approx_censored_add_mult.py:1041-1066 and :341-352;
+    ``likelihood`` is the reference object or its mirror (same attribute names)."""
+    N, L = log_f.shape
+    full = lambda a: np.broadcast_to(np.asarray(a, dtype=np.float64), (N, L))      # noqa: E731
+    y, sa, sm, om = full(likelihood.y), full(likelihood.sigma_a), full(likelihood.sigma_m), full(likelihood.omega)
+    fm1, fp1 = full(likelihood.log_fm1), full(likelihood.log_fp1)
+    sm2 = sm ** 2
+    s_a = sa * np.sqrt(np.expm1(sm2) * np.exp(2.0 * (log_f - np.log(sa))) + 1.0)
+    m_m = -0.5 * (sm2 + np.log1p(np.exp(2.0 * (np.log(sa) - log_f - sm2 / 2.0))))
+    s_m2 = -2.0 * m_m
+    u = np.clip((log_f - fm1) / (fp1 - fm1), 0.0, 1.0)
+    lam = np.where(log_f <= fm1, 1.0, np.where(log_f >= fp1, 0.0, ((-6.0 * u + 15.0) * u - 10.0) * u ** 3 + 1.0))
+    return {"censored_mask": (y <= om) * 1, "sigma_a": sa * 1, "sigma_m": sm * 1, "m_a": np.zeros((N, L)), "s_a": s_a,
+            "s_a2": s_a ** 2, "m_m": m_m, "s_m2": s_m2, "s_m": np.sqrt(s_m2), "lambda_": lam}
+
+
 class SmoothIndicatorPrior:
     """Mirror of priors/smooth_indicator_prior.py:113-166 (attributes only)."""
 

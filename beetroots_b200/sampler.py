@@ -56,7 +56,7 @@ class B200Sampler:
 
     def __init__(self, my_sampler_params, D: int, L: int, N: int,
                  rng: np.random.Generator = None, device: int = 0, mlp_mode: int = MLP_FP32,
-                 device_chain: int = 0, device_chain_thin: int = 1):
+                 device_chain: int = 0, device_chain_thin: int = 1, saver_nll_utils: Optional[bool] = None):
         p = my_sampler_params
         self.eps0 = p.initial_step_size
         self.lambda_ = p.extreme_grad
@@ -90,6 +90,10 @@ class B200Sampler:
         assert device_chain >= 0 and device_chain_thin >= 1
         self.device_chain = int(device_chain)
         self.device_chain_thin = int(device_chain_thin)
+        # the reference hands the saver the per-(pixel, line) likelihood auxiliaries (s_a, m_m, lambda_, ...: my_saver.py:57-61);
+        # here they are re-evaluated on the host from ln f of the saved iterate.  None: only for maps up to 10^6 (pixel, line)
+        # pairs (ten float64 arrays of that size per saved iterate -- 0.8 GB at c4 -- are rarely wanted)
+        self.saver_nll_utils = saver_nll_utils
         self._dev: Optional[DevicePosterior] = None
         self._dev_owner = None
 
@@ -167,15 +171,22 @@ class B200Sampler:
         except TypeError:                                  # sharded / stand-in devices without the option
             Theta, v, _ = dev.get_state(want_v=True, want_j=False)
         if Theta is None:                                  # sharded run, not the root rank
-            if getattr(saver, "save_forward_map_evals", True):
+            want_aux = self.saver_nll_utils if self.saver_nll_utils is not None else self.N * self.L <= 1_000_000
+            if getattr(saver, "save_forward_map_evals", True) or want_aux:
                 dev.get_log_f()                            # take part in the gather
             return False
         self.v = v.reshape(-1)
-        fm = {}
-        if getattr(saver, "save_forward_map_evals", True):
+        want_aux = self.saver_nll_utils if self.saver_nll_utils is not None else self.N * self.L <= 1_000_000
+        fm, aux = {}, {}
+        if getattr(saver, "save_forward_map_evals", True) or want_aux:
             log_f = dev.get_log_f()
-            fm = {"log_f_Theta": log_f, "f_Theta": np.exp(log_f)}
-        self.current = {"Theta": Theta, "forward_map_evals": fm, "nll_utils": {"nll": np.float64(dict_objective["nll"])}}
+            if getattr(saver, "save_forward_map_evals", True):
+                fm = {"log_f_Theta": log_f, "f_Theta": np.exp(log_f)}
+            if want_aux:
+                from .modelling import saver_nll_utils
+                aux = saver_nll_utils(self._dev_owner.likelihood, log_f)
+        self.current = {"Theta": Theta, "forward_map_evals": fm,
+                        "nll_utils": {"nll": np.float64(dict_objective["nll"]), **aux}}
         return True
 
     # ------------------------------------------------------------------ kernels

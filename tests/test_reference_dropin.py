@@ -52,3 +52,22 @@ def test_b200_sampler_has_the_reference_signature():
     for m in ("generate_new_sample_mtm", "generate_new_sample_pmala_rmsprop", "get_rng_state", "set_rng_state",
               "generate_random_start_Theta", "generate_random_start_Theta_1pix"):
         assert hasattr(B200Sampler, m)
+
+
+def test_saver_auxiliaries_equal_the_reference_nll_utils(built_lib):
+    """beetroots_b200.modelling.saver_nll_utils (host glue for the Saver hand-over) against the unmodified reference's
+    ``MixingModelsLikelihood.evaluate_all_nll_utils`` at the same Theta: every (N, L) entry the reference saver stores."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as MG
+    from beetroots_b200.modelling import saver_nll_utils
+    ref_post, post, inputs = MG.build_case(H=6, W=5, L=7, K=3, nnn=False, seed=4, censor_boost=2.5)
+    cur = ref_post.compute_all(inputs["theta0"] * 1, compute_derivatives_2nd_order=False)
+    log_f = cur["forward_map_evals"]["log_f_Theta"]
+    stored = {k for k in cur["nll_utils"] if "nll_" not in k and "grad" not in k and "hess_diag" not in k
+              and np.ndim(cur["nll_utils"][k]) == 2}
+    for lik in (ref_post.likelihood, post.likelihood):              # the reference object and its mirror
+        aux = saver_nll_utils(lik, log_f)
+        assert set(aux) == stored, (set(aux) ^ stored)
+        for k in stored:
+            np.testing.assert_allclose(aux[k], cur["nll_utils"][k], rtol=1e-12, atol=1e-300, err_msg=k)
+    assert 0.05 < aux["censored_mask"].mean() < 0.95 and 0 < aux["lambda_"].min() < aux["lambda_"].max() <= 1
