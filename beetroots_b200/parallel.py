@@ -39,6 +39,7 @@ class BandPlan:
     send_down: Optional[np.ndarray]  # local ids of my last owned row   (-> rank + 1)
     recv_up: Optional[np.ndarray]    # local ids of the ghost row above (<- rank - 1)
     recv_down: Optional[np.ndarray]  # local ids of the ghost row below (<- rank + 1)
+    owned_gid_by_rank: Optional[list] = None   # global ids of the pixels every rank owns, in that rank's local order (gathers)
 
     @property
     def n_local(self) -> int:
@@ -71,6 +72,41 @@ def make_band_plan(H: int, W: int, world: int, rank: int) -> BandPlan:
                     local_row(r1) if rank < world - 1 else None)
 
 
+def make_band_plan_xy(X: np.ndarray, Y: np.ndarray, world: int, rank: int) -> BandPlan:
+    """Row bands of an arbitrary (non-rectangular, arbitrarily ordered) pixel set given by its index coordinates, as the
+    reference's maps are (abstract_spatial_prior.py:13-55: an edge exists only between pixels that are both in the index).
+    Bands = contiguous groups of the distinct X values (balanced in rows); ghosts = the pixels of the rows X_first - 1 and
+    X_last + 1 where those rows exist; local order = ascending global pixel id (so that neighbour order and colour classes
+    of owned pixels are those of the full map); rows on the two sides of a cut are listed by ascending global id on both
+    ranks, which is what pairs the halo buffers."""
+    X, Y = np.asarray(X).astype(np.int64), np.asarray(Y).astype(np.int64)
+    rows = np.unique(X)
+    assert 1 <= world <= rows.size, "need at least one row per rank"
+    bounds = [band_rows(rows.size, world, r) for r in range(world)]
+    gids = np.arange(X.size, dtype=np.int64)
+
+    def owned_of(r):
+        a, b = bounds[r]
+        return gids[(X >= rows[a]) & (X <= rows[b - 1]) & np.isin(X, rows[a:b])]
+
+    a, b = bounds[rank]
+    x_first, x_last = rows[a], rows[b - 1]
+    has_up = rank > 0 and rows[a - 1] == x_first - 1              # the row above the cut exists and touches mine
+    has_down = rank < world - 1 and rows[b] == x_last + 1
+    own = np.isin(X, rows[a:b])
+    ghost_up = (X == x_first - 1) if has_up else np.zeros(X.size, bool)
+    ghost_down = (X == x_last + 1) if has_down else np.zeros(X.size, bool)
+    stored = gids[own | ghost_up | ghost_down]                       # ascending global id
+    loc = {int(g): i for i, g in enumerate(stored)}
+    ids = lambda m: np.array([loc[int(g)] for g in gids[m]], dtype=np.int32)      # noqa: E731
+    owned = own[stored].astype(np.uint8)
+    return BandPlan(int(rows.size), int(Y.max() - Y.min() + 1), world, rank, int(x_first), int(x_last) + 1,
+                    int(x_first) - (1 if has_up else 0), int(x_last) + 1 + (1 if has_down else 0), stored, owned,
+                    ids(own & (X == x_first)) if has_up else None, ids(own & (X == x_last)) if has_down else None,
+                    ids(ghost_up) if has_up else None, ids(ghost_down) if has_down else None,
+                    [owned_of(r) for r in range(world)])
+
+
 def exchange_halo(plan: BandPlan, gather: Callable, scatter: Callable, dist, make_buffer: Callable):
     """One halo exchange.  ``gather(name) -> tensor (W, D)`` reads the rows ``plan.<name>`` of the local
     state (name in send_up / send_down), ``scatter(name, tensor)`` writes the rows ``plan.<name>`` (recv_up /
@@ -81,12 +117,12 @@ def exchange_halo(plan: BandPlan, gather: Callable, scatter: Callable, dist, mak
     ops, recvs = [], []
     if plan.send_up is not None:
         ops.append(dist.P2POp(dist.isend, gather("send_up"), plan.rank - 1))
-        buf = make_buffer()
+        buf = _buffer(make_buffer, "recv_up")
         ops.append(dist.P2POp(dist.irecv, buf, plan.rank - 1))
         recvs.append(("recv_up", buf))
     if plan.send_down is not None:
         ops.append(dist.P2POp(dist.isend, gather("send_down"), plan.rank + 1))
-        buf = make_buffer()
+        buf = _buffer(make_buffer, "recv_down")
         ops.append(dist.P2POp(dist.irecv, buf, plan.rank + 1))
         recvs.append(("recv_down", buf))
     for req in dist.batch_isend_irecv(ops):
@@ -95,7 +131,16 @@ def exchange_halo(plan: BandPlan, gather: Callable, scatter: Callable, dist, mak
         scatter(name, buf)
 
 
-def local_posterior(post, plan: BandPlan):
+def _buffer(make_buffer, name):
+    """Receive buffer for the ghost row ``name``; ``make_buffer`` may take the name (rows of different lengths on
+    non-rectangular maps) or nothing (full rectangle: every row has W pixels)."""
+    try:
+        return make_buffer(name)
+    except TypeError:
+        return make_buffer()
+
+
+def local_posterior(post, plan: BandPlan, X=None, Y=None):
     """Sub-problem of one band: observations sliced, prior graph rebuilt on the stored rows (global
     coordinates, so colours and neighbour order are those of the full map), colour classes restricted to
     the owned pixels."""
@@ -105,7 +150,10 @@ def local_posterior(post, plan: BandPlan):
     lik_loc = M.MixingModelsLikelihood(lik.forward_map, post.D, post.L, n_loc, lik.y[gid], lik.sigma_a[gid],
                                        lik.sigma_m[gid], lik.omega[gid], lik.log_fm1[gid], lik.log_fp1[gid])
     ps = post.prior_spatial
-    X, Y = gid // plan.W, gid % plan.W
+    if X is None:
+        X, Y = gid // plan.W, gid % plan.W
+    else:
+        X, Y = np.asarray(X)[gid], np.asarray(Y)[gid]
     sp = None
     sites: Dict[int, np.ndarray]
     if ps is not None:
@@ -120,19 +168,25 @@ def local_posterior(post, plan: BandPlan):
 class ShardedDevicePosterior:
     """Same surface as DevicePosterior for B200Sampler, over ``torch.distributed`` ranks (one per GPU)."""
 
-    def __init__(self, posterior, H: int, W: int, device: int = 0, mlp_mode: int = MLP_FP32):
+    def __init__(self, posterior, H: int, W: int, device: int = 0, mlp_mode: int = MLP_FP32, X=None, Y=None):
+        """``X``, ``Y``: index coordinates of the pixels (any order, the map need not be a full rectangle); omitted for a
+        full H x W map in row-major (X slow) order."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        assert posterior.N == H * W, "row-band sharding needs a full H x W map in row-major (X slow) order"
         self.N, self.D, self.L = posterior.N, posterior.D, posterior.L
-        self.plan = make_band_plan(H, W, self.world, self.rank)
+        if X is None:
+            assert posterior.N == H * W, "without X, Y the map must be a full H x W rectangle in row-major (X slow) order"
+            self.plan = make_band_plan(H, W, self.world, self.rank)
+        else:
+            assert len(X) == len(Y) == posterior.N
+            self.plan = make_band_plan_xy(X, Y, self.world, self.rank)
         if self.world == 1:
             self.local = DevicePosterior.from_posterior(posterior, device=device, mlp_mode=mlp_mode)
         else:
-            post_loc, sites = local_posterior(posterior, self.plan)
+            post_loc, sites = local_posterior(posterior, self.plan, X, Y)
             self.local = DevicePosterior.from_posterior(post_loc, device=device, global_id=self.plan.local_global_id,
                                                         dict_sites=sites, mlp_mode=mlp_mode)
         self.n_sites, self.site_keys = self.local.n_sites, self.local.site_keys
@@ -166,8 +220,8 @@ class ShardedDevicePosterior:
             buf = buf.to(self.dev)
             self.local.scatter_theta_rows(t.data_ptr(), t.numel(), buf.data_ptr())
 
-        def make_buffer():
-            return torch.empty((self.plan.W, self.D), dtype=torch.float32, device=self.coll_dev)
+        def make_buffer(name):
+            return torch.empty((self._ids[name].numel(), self.D), dtype=torch.float32, device=self.coll_dev)
 
         exchange_halo(self.plan, gather, scatter, self.dist, make_buffer)
 
@@ -301,9 +355,13 @@ class ShardedDevicePosterior:
             return local_arr
         torch = self.torch
         own = local_arr[self.plan.owned > 0]
-        sizes = [(band_rows(self.plan.H, self.world, r)[1] - band_rows(self.plan.H, self.world, r)[0]) * self.plan.W
-                 for r in range(self.world)]
-        # bands may differ by one row: gather equal-sized (zero-padded) pieces and trim, which every backend supports
+        by_rank = self.plan.owned_gid_by_rank
+        if by_rank is not None:
+            sizes = [int(g.size) for g in by_rank]
+        else:
+            sizes = [(band_rows(self.plan.H, self.world, r)[1] - band_rows(self.plan.H, self.world, r)[0]) * self.plan.W
+                     for r in range(self.world)]
+        # bands differ in size: gather equal-sized (zero-padded) pieces and trim, which every backend supports
         smax = max(sizes)
         mine = torch.zeros((smax,) + tuple(own.shape[1:]), dtype=torch.as_tensor(own).dtype, device=self.coll_dev)
         mine[:own.shape[0]] = torch.as_tensor(np.ascontiguousarray(own), device=self.coll_dev)
@@ -315,7 +373,12 @@ class ShardedDevicePosterior:
             self.dist.gather(mine, outs, dst=0)
             if self.rank != 0:
                 return None
-        return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0).cpu().numpy()
+        cat = torch.cat([o[:s] for o, s in zip(outs, sizes)], 0).cpu().numpy()
+        if by_rank is None:
+            return cat                                     # full rectangle: bands in rank order = global pixel order
+        out = np.empty_like(cat)
+        out[np.concatenate(by_rank)] = cat                 # any pixel order: back to the global ids
+        return out
 
     def get_log_f(self):
         return self._gather_owned(self.local.get_log_f())

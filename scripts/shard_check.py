@@ -33,7 +33,24 @@ mlp = MLP_BF16_TC if mode in ("bf16", "samplebf16") else MLP_FP32
 NEXT = mode == "next"          # fp32 + the "next" rows: chain store, optimisation mode, regularisation-weight update
 prob = make_problem(H, W, lambda fm, th: gpu_log_f(fm, th, device=local), L=10, k_mtm=K, use_next_nearest_neighbors=(mode == "fp32n8"))
 post = prob.posterior
-sdev = ShardedDevicePosterior(post, H, W, device=local, mlp_mode=mlp)
+XY = {}
+if mode == "mask":
+    # a non-rectangular, shuffled map (abstract_spatial_prior.py:13-55): pixels and a corner removed, one empty row
+    from beetroots_b200 import modelling as M
+    X0, Y0 = np.repeat(np.arange(H), W), np.tile(np.arange(W), H)
+    keep = np.ones(H * W, bool)
+    keep[[7, 20, 333]] = False
+    keep[(X0 >= 30) & (Y0 >= 15)] = False
+    keep[X0 == 18] = False
+    sel = np.where(keep)[0][np.random.default_rng(3).permutation(int(keep.sum()))]
+    lik, n = post.likelihood, sel.size
+    lik2 = M.MixingModelsLikelihood(lik.forward_map, post.D, post.L, n, lik.y[sel], lik.sigma_a[sel], lik.sigma_m[sel],
+                                    lik.omega[sel], lik.log_fm1[sel], lik.log_fp1[sel])
+    sp2 = M.L22DiscreteGradSpatialPrior(post.D, n, X0[sel], Y0[sel], None, False, post.prior_spatial.initial_weights)
+    post = M.Posterior(post.D, post.L, n, lik2, sp2, post.prior_indicator)
+    prob.theta_init = prob.theta_init[sel]
+    XY = dict(X=X0[sel], Y=Y0[sel])
+sdev = ShardedDevicePosterior(post, H, W, device=local, mlp_mode=mlp, **XY)
 smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N, device=local, mlp_mode=mlp)
 smp.attach(post, sdev)
 smp.philox_seed = 777

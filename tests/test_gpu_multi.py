@@ -49,7 +49,7 @@ def _compare(a, b, mode, what):
         assert np.allclose(a["s_obj"], b["s_obj"], rtol=1e-6) and np.allclose(a["s_acc"], b["s_acc"], atol=2.0 / 800)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16", "next", "sample", "samplebf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "next", "sample", "samplebf16", "mask"])
 def test_sharded_chain_on_one_gpu_is_bit_identical(tmp_path, built_lib, mode):
     """Runs on a single-GPU machine: 3 ranks share GPU 0, each owns a row band (own context, ghost rows), the halo
     exchange and the global reductions go through gloo on the host -- the band plan, exchange and reduction code is the one
@@ -61,7 +61,7 @@ def test_sharded_chain_on_one_gpu_is_bit_identical(tmp_path, built_lib, mode):
     _compare(np.load(ref), np.load(out), mode, "3 bands on one GPU")
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32n8", "bf16", "next", "sample"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32n8", "bf16", "next", "sample", "mask"])
 def test_sharded_chain_is_bit_identical(tmp_path, built_lib, mode):
     import torch
     n = torch.cuda.device_count()

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from beetroots_b200 import modelling as M
-from beetroots_b200.parallel import band_rows, exchange_halo, local_posterior, make_band_plan
+from beetroots_b200.parallel import band_rows, exchange_halo, local_posterior, make_band_plan, make_band_plan_xy
 
 
 def test_band_plan_partitions_the_map():
@@ -57,6 +57,60 @@ def test_local_graph_is_sharding_invariant(nnn):
                 for n in loc:
                     mine = nbl[n][nbl[n] >= 0]
                     assert np.array_equal(gid[mine], nbr[gid[n]][nbr[gid[n]] >= 0])
+
+
+def test_general_band_plan_equals_the_rectangular_one_and_handles_masks():
+    """make_band_plan_xy on a full rectangle reproduces make_band_plan; on a non-rectangular, shuffled pixel set (the maps of
+    abstract_spatial_prior.py:13-55) every pixel is owned exactly once, the ghost rows are the neighbouring rows that exist,
+    the two sides of a cut list the same pixels in the same order, and the local graph of every band keeps the neighbour
+    order and colours of the full map."""
+    H, W, D, L = 9, 6, 4, 3
+    X, Y = np.repeat(np.arange(H), W), np.tile(np.arange(W), H)
+    for world in (1, 2, 4):
+        for r in range(world):
+            a, b = make_band_plan(H, W, world, r), make_band_plan_xy(X, Y, world, r)
+            assert np.array_equal(a.local_global_id, b.local_global_id) and np.array_equal(a.owned, b.owned)
+            for k in ("send_up", "send_down", "recv_up", "recv_down"):
+                assert (getattr(a, k) is None) == (getattr(b, k) is None)
+                assert getattr(a, k) is None or np.array_equal(getattr(a, k), getattr(b, k))
+    # a masked, shuffled map: two pixels and a whole corner removed, one empty row in the middle (bands without coupling)
+    keep = np.ones(H * W, bool)
+    keep[[7, 20]] = False
+    keep[(X >= 7) & (Y >= 4)] = False
+    keep[X == 4] = False
+    perm = np.random.default_rng(3).permutation(int(keep.sum()))
+    Xm, Ym = X[keep][perm], Y[keep][perm]
+    N = Xm.size
+    for nnn in (False, True):
+        sp = M.L22DiscreteGradSpatialPrior(D, N, Xm, Ym, None, nnn, np.ones(D))
+        lik = M.MixingModelsLikelihood(None, D, L, N, np.ones((N, L)), 1.0, 0.1, 0.5, a0=np.zeros((1, L)), a1=np.ones((1, L)))
+        post = M.Posterior(D, L, N, lik, sp, None)
+        deg = 8 if nnn else 4
+        nbr = M.build_neighbor_table(sp.list_edges, N, deg)
+        colour_of = np.zeros(N, dtype=int)
+        for k, v in sp.dict_sites.items():
+            colour_of[v] = k
+        for world in (2, 3):
+            plans = [make_band_plan_xy(Xm, Ym, world, r) for r in range(world)]
+            seen = np.zeros(N, int)
+            for r, plan in enumerate(plans):
+                gid = plan.local_global_id
+                seen[gid[plan.owned > 0]] += 1
+                assert np.array_equal(gid[plan.owned > 0], plan.owned_gid_by_rank[r])
+                if plan.send_down is not None:                       # my last row <-> the ghost row above of the next rank
+                    nxt = plans[r + 1]
+                    assert np.array_equal(gid[plan.send_down], nxt.local_global_id[nxt.recv_up])
+                    assert np.array_equal(gid[plan.recv_down], nxt.local_global_id[nxt.send_up])
+                else:
+                    assert r == world - 1 or plans[r + 1].recv_up is None
+                lp, sites = local_posterior(post, plan, Xm, Ym)
+                nbl = M.build_neighbor_table(lp.prior_spatial.list_edges, plan.n_local, deg)
+                for k, loc in sites.items():
+                    assert np.all(plan.owned[loc] == 1) and np.all(colour_of[gid[loc]] == k)
+                    for n in loc:
+                        mine = nbl[n][nbl[n] >= 0]
+                        assert np.array_equal(gid[mine], nbr[gid[n]][nbr[gid[n]] >= 0])
+            assert np.all(seen == 1)
 
 
 def _free_port():
