@@ -329,7 +329,7 @@ def run_ours(args):
         e2e_sample = {}
         n_it = 20            # (a multiple of both freq_save values: MySaver sizes its last batch (T_MC - t + 1) // freq_save)
         for freq in (1, 10):
-            saver = DiscardingSaver(post.N, post.D, post.D, post.L, results_path="", batch_size=2, freq_save=freq,
+            saver = DiscardingSaver(post.N, post.D, post.D, post.L, results_path="", batch_size=10 // freq, freq_save=freq,
                                     save_forward_map_evals=False)
             smp2 = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N,
                                rng=np.random.default_rng(43), device=local, mlp_mode=mode)
@@ -348,7 +348,8 @@ def run_ours(args):
                                                "seconds": dt}
         e2e_sample["note"] = ("B200Sampler.sample() incl. the initial compute_all, kernel-type draws, objective terms, model check, "
                               "float64 hand-over of Theta and v to an in-memory Saver (ChainSaver, save_forward_map_evals=False, "
-                              "batch_size=2) and the final state pull / save_additional")
+                              "batches of 10 iterations) and the final state pull / save_additional; about 4/5 of the per-iterate "
+                              "hand-over time is the saver's own host copies (33 MB float64 arrays at c4), as in the reference's MySaver")
         # ---- the reference's own K_mtm values at N >= 64^2 (nn_N64_fixed_angle.yaml:97): device-resident, same timing rules
         sdev.compute_all(prob.theta_init)
         sdev.init_v_from_grad()
