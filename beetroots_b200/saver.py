@@ -72,21 +72,35 @@ class ChainSaver:
         self.t_last_init = t * 1
         self.next_batch_size = min(self.batch_size, (T_MC - t + 1) // self.freq_save)
         self.final_next_batch_size = B = self.next_batch_size
-        mem = {"list_Theta": np.zeros((B, self.N, self.D_sampling))}
+        pool = getattr(self, "_pool", {})                           # batch arrays of the previous save (already written out)
+
+        def zeros(name, shape, dtype=np.float64):
+            # a fresh 0.3 GB batch array at c4 costs ~80 ms of page faults; the previous batch's array is re-zeroed instead
+            a = pool.get(name)
+            if a is not None and a.shape == tuple(shape) and a.dtype == dtype:
+                a.fill(0)
+                return a
+            return np.zeros(shape, dtype=dtype)
+
+        mem = {"list_Theta": zeros("list_Theta", (B, self.N, self.D_sampling))}
         for k, v in self._entries(forward_map_evals, nll_utils, dict_objective, additional_sampling_log):
-            mem[f"list_{k}"] = np.zeros((B,) + (np.shape(v) if isinstance(v, np.ndarray) or hasattr(v, "shape") else ()))
-        mem["list_rng_state"] = np.zeros((B, 32), dtype=np.uint8)
-        mem["list_rng_inc"] = np.zeros((B, 32), dtype=np.uint8)
+            mem[f"list_{k}"] = zeros(f"list_{k}", (B,) + tuple(np.shape(v) if isinstance(v, np.ndarray) or hasattr(v, "shape") else ()))
+        mem["list_rng_state"] = zeros("list_rng_state", (B, 32), np.uint8)
+        mem["list_rng_inc"] = zeros("list_rng_inc", (B, 32), np.uint8)
         self.memory = mem
+        self._pool = {}
 
     def update_memory(self, t: int, Theta: np.ndarray, forward_map_evals: dict = {}, nll_utils: dict = {},
                       dict_objective: dict = {}, additional_sampling_log: dict = {},
                       rng_state_array: Optional[np.ndarray] = None, rng_inc_array: Optional[np.ndarray] = None) -> None:
         slot = (t - self.t_last_init) // self.freq_save
-        full = np.zeros((Theta.shape[0], self.D))
-        full[:, self.list_idx_sampling] = Theta                      # sampled parameters in their columns, the rest 0
-        lin = self.scaler.from_scaled_to_lin(full) if self.scaler is not None else full
-        self.memory["list_Theta"][slot] = lin[:, self.list_idx_sampling]
+        if self.scaler is None and self.D_sampling == self.D and np.array_equal(self.list_idx_sampling, np.arange(self.D)):
+            self.memory["list_Theta"][slot] = Theta                  # nothing to place or to transform: one copy (33 MB at c4)
+        else:
+            full = np.zeros((Theta.shape[0], self.D))
+            full[:, self.list_idx_sampling] = Theta                  # sampled parameters in their columns, the rest 0
+            lin = self.scaler.from_scaled_to_lin(full) if self.scaler is not None else full
+            self.memory["list_Theta"][slot] = lin[:, self.list_idx_sampling]
         for k, v in self._entries(forward_map_evals, nll_utils, dict_objective, additional_sampling_log):
             if k not in ("m_a", "s_a", "m_m", "s_m") or k not in dict_objective:
                 self.memory[f"list_{k}"][slot] = v
@@ -120,6 +134,7 @@ class ChainSaver:
                 self.saved[k] = v.copy() if (self.t_last_init == 1 or k not in self.saved) else np.concatenate([self.saved[k], v], 0)
             if self.results_path:
                 np.savez(os.path.join(self.results_path, "mc_chains.npz"), **self.saved)
+        self._pool = self.memory                                     # (copied / written above: reusable for the next batch)
         self.memory = dict()
 
     def save_additional(self, list_arrays: List[np.ndarray], list_names: List[str]) -> None:

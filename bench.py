@@ -324,6 +324,7 @@ def run_ours(args):
             being appended to a file, so the number measures the sampler's hand-over, not a disk."""
 
             def save_to_file(self):
+                self._pool = self.memory
                 self.memory = dict()
 
         e2e_sample = {}

@@ -10,6 +10,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
 def _run(world, out, mode, one_gpu=False):
     script = os.path.join(ROOT, "scripts", "shard_check.py")
     env = dict(os.environ)
@@ -19,7 +28,7 @@ def _run(world, out, mode, one_gpu=False):
         cmd = [sys.executable, script, out, mode]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-               "--master-addr", "127.0.0.1", "--master-port", "29517", script, out, mode]
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), script, out, mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 

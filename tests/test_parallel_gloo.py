@@ -121,6 +121,20 @@ def _free_port():
     return p
 
 
+def _spawn(fn, make_args, nprocs, tries=3):
+    """mp.spawn with a fresh rendezvous port per attempt: between _free_port() closing its probe socket and rank 0 binding the
+    port another process can take it (rare, but the suite runs with -x)."""
+    for attempt in range(tries):
+        try:
+            mp.spawn(fn, args=make_args(_free_port()), nprocs=nprocs, join=True)
+            return
+        except Exception as e:                                    # noqa: BLE001
+            msg = str(e)
+            if attempt == tries - 1 or not any(k in msg for k in ("Address already in use", "EADDRINUSE", "Connection refused",
+                                                                  "connect() timed out", "Socket Timeout")):
+                raise
+
+
 def _worker(rank, world, port, H, W, D, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -151,7 +165,7 @@ def _worker(rank, world, port, H, W, D, out_dir):
 @pytest.mark.parametrize("world", [2, 3])
 def test_halo_exchange_gloo(tmp_path, world):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, 7, 4, 3, str(tmp_path)), nprocs=world, join=True)
+    _spawn(_worker, lambda p: (world, p, 7, 4, 3, str(tmp_path)), world)
     for r in range(world):
         assert np.load(tmp_path / f"ok{r}.npy")[0]
 
@@ -224,7 +238,7 @@ def _reduction_worker(rank, world, port, H, W, out_dir):
 @pytest.mark.parametrize("world", [2, 3])
 def test_global_reductions_of_the_next_rows_gloo(tmp_path, world):
     port = _free_port()
-    mp.spawn(_reduction_worker, args=(world, port, 9, 5, str(tmp_path)), nprocs=world, join=True)
+    _spawn(_reduction_worker, lambda p: (world, p, 9, 5, str(tmp_path)), world)
     for r in range(world):
         assert np.load(tmp_path / f"red{r}.npy")[0]
 
@@ -305,7 +319,7 @@ def test_sample_on_several_ranks_has_one_writer(tmp_path, world):
     concurrent writers), every rank runs the kernels the ROOT drew with the ROOT's Philox key and takes the same saver
     branches (identical call sequences: no deadlock in the collectives behind them)."""
     port = _free_port()
-    mp.spawn(_sample_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    _spawn(_sample_worker, lambda p: (world, p, str(tmp_path)), world)
     k0 = np.load(tmp_path / "kinds0.npy")
     for r in range(1, world):
         assert np.array_equal(np.load(tmp_path / f"kinds{r}.npy"), k0)
