@@ -41,8 +41,8 @@ class ChainSaver:
 
     def set_results_path(self, results_path: str) -> None:
         self.results_path = results_path
-        if len(results_path) > 0 and not os.path.isdir(results_path):
-            os.mkdir(results_path)
+        if len(results_path) > 0:
+            os.makedirs(results_path, exist_ok=True)             # (several ranks may construct their saver at the same time)
 
     # ---- when (abstract_saver.py:130-163)
     def check_need_to_save(self, t: int) -> bool:
