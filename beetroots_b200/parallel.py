@@ -348,13 +348,17 @@ class ShardedDevicePosterior:
     def reserve_scratch(self, max_rows, max_rows_with_jacobian=0):
         self.local.reserve_scratch(max_rows, max_rows_with_jacobian)
 
-    def _gather_owned(self, local_arr, everywhere=False):
+    def _gather_owned(self, local_arr, everywhere=False, f32_exact=False):
         """(N_loc, ...) -> (N, ...) on the root rank (None elsewhere); on every rank if ``everywhere``.  Only the root
         talks to the saver, so by default nothing is shipped to, or copied off the device on, the other ranks."""
         if self.world == 1:
             return local_arr
         torch = self.torch
         own = local_arr[self.plan.owned > 0]
+        # ``f32_exact``: a float64 array whose values are float32 numbers (Theta, v: float32 on the device) travels as float32
+        as_f32 = f32_exact and own.dtype == np.float64
+        if as_f32:
+            own = own.astype(np.float32)
         by_rank = self.plan.owned_gid_by_rank
         if by_rank is not None:
             sizes = [int(g.size) for g in by_rank]
@@ -374,6 +378,8 @@ class ShardedDevicePosterior:
             if self.rank != 0:
                 return None
         cat = torch.cat([o[:s] for o, s in zip(outs, sizes)], 0).cpu().numpy()
+        if as_f32:
+            cat = cat.astype(np.float64)
         if by_rank is None:
             return cat                                     # full rectangle: bands in rank order = global pixel order
         out = np.empty_like(cat)
@@ -385,7 +391,7 @@ class ShardedDevicePosterior:
 
     def get_state(self, want_v=True, want_j=True):
         th, v, j = self.local.get_state(want_v, want_j)
-        return (self._gather_owned(th), self._gather_owned(v) if want_v else None,
+        return (self._gather_owned(th, f32_exact=True), self._gather_owned(v, f32_exact=True) if want_v else None,
                 self._gather_owned(j) if want_j else None)
 
     def get_current(self, with_forward_map=True):
