@@ -388,3 +388,36 @@ def test_sample_in_optimisation_mode(lib):
     np.testing.assert_allclose(clppd, np.exp(-nll_full), rtol=2e-4, atol=1e-30)
     assert np.all((pvy >= 0) & (pvy <= 0.5)) and np.all((pvl >= 0) & (pvl <= 1))
     assert np.allclose(pvy * 40, np.round(pvy * 40), atol=1e-3) and pvl.std() > 0
+
+
+def test_kernel_profile_and_scratch_reservation(built_lib):
+    """bt_reserve_scratch / bt_kernel_profile (the measurement hooks of bench.py): after the reservation a step allocates nothing
+    (the scratch pointers are stable), and the per-kernel timers return positive device times with the algorithmic bytes of
+    the launch shapes."""
+    from beetroots_b200 import MLP_BF16_TC, B200Sampler, DevicePosterior, MySamplerParams
+    from beetroots_b200.synthetic import make_problem
+    from oracle import posterior as OP
+    K = 6
+    prob = make_problem(24, 20, lambda fm, th: OP.forward_map_compute_all(fm, th, False)["log_f_Theta"], L=10, k_mtm=K)
+    post = prob.posterior
+    dev = DevicePosterior.from_posterior(post, mlp_mode=MLP_BF16_TC)
+    n_max = max(p.size for p in dev.site_pixels)
+    dev.reserve_scratch(n_max * (K + 1), post.N)
+    dev.compute_all(prob.theta_init)
+    dev.init_v_from_grad()
+    smp = B200Sampler(MySamplerParams(1e-4, 1e-5, 0.99, [0.5, 0.5], K, True, False), post.D, post.L, post.N, mlp_mode=MLP_BF16_TC)
+    smp.attach(post, dev)
+    smp.philox_seed = 5
+    dev.kernel_profile(enable=True, reset=True)
+    smp.generate_new_sample_mtm(1, post)
+    smp.generate_new_sample_pmala_rmsprop(2, post)
+    prof = dev.kernel_profile(enable=False, reset=True)
+    n_pix = post.N // 2
+    for name in ("pmala_propose", "pmala_accept", "mtm_gen", "mtm_nl", "mtm_select"):
+        ms, nbytes, launches = prof[name]
+        assert launches == 2 and ms > 0 and nbytes > 0, (name, prof[name])
+    # candidate rows written by mtm_gen: n_pix x K rows of D floats per colour class, plus theta + stencil per pixel
+    assert prof["mtm_gen"][1] >= 2 * n_pix * K * post.D * 4
+    assert prof["mtm_nl"][1] > prof["mtm_select"][1] > 0
+    assert dev.kernel_profile(enable=False)["mtm_nl"][2] == 0          # reset
+    dev.close()
