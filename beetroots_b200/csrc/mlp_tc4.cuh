@@ -62,6 +62,9 @@
 #define TC4_MISC_BYTES (1024 + TC4_NEW * 512)    // barriers + one 32 x 8 bf16 transposition tile per epilogue warp
 #define TC4_OUT_PAD 16
 #define TC4_MAX_SEGS 64
+#ifndef TC4_PAIR_STEPS
+#define TC4_PAIR_STEPS 2              // steps issued per pass through the elected-lane region (1: one; 3 and 4 measured: no further gain)
+#endif
 #define TC4_F_ACC0 1               // first MMA of the step overwrites the accumulator
 #define TC4_F_WAIT_IN 2            // wait for the tile's input K-blocks
 #define TC4_F_KBFREE 4             // after this step nothing of this tile reads the input K-blocks any more
@@ -683,11 +686,55 @@ mlp_tc4_kernel(const __grid_constant__ Tc4Sched sch, FmapDev fm, const float* __
                         tc_fence_after();
                         if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0 && step_no < 240) dbg[240 + step_no] = ready;
                     }
-                    --ready;
                     if (DBG == 1 && dbg && blockIdx.x == 0 && tl == 1 && lane == 0 && step_no < 240) dbg[step_no] = clock64();
                     if (DBG == 1) ++step_no;
                     const uint32_t a_lo = act_lo + (uint32_t)kb * (TC_KB_BYTES >> 4), b_lo = ring_lo + slot * slot_lo;
                     const int lo = kb == sg.kb0 ? sg.ks_lo : 0, hi = kb == kb_last ? sg.ks_hi : 4;
+#if TC4_PAIR_STEPS
+                    // several whole steps of the segment in ONE pass through the elected-lane region (4 MMAs + 1 commit each, one
+                    // reconvergence for all) when their weights have landed: entering the region costs more than the MMAs of a
+                    // step (scripts/umma3_bench.cu part F).  Unrolled for 4 / 3 / 2 steps: a loop inside the region does not pay
+                    // (profiles/r02_microbench.txt, batch-wise issuer).
+                    {
+                        int whole = kb_last - kb + 1;                // steps left in the segment ...
+                        if (sg.ks_hi != 4) --whole;                  // ... that use all four 16-feature slices of their K-block
+                        int m = lo == 0 ? (whole < (int)ready ? whole : (int)ready) : 0;
+                        if (m > TC4_PAIR_STEPS) m = TC4_PAIR_STEPS;
+                        if (m >= 2) {
+                            uint32_t sl[4], bl[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t x = slot + (uint32_t)j;
+                                if (x >= (uint32_t)n_slots) x -= (uint32_t)n_slots;
+                                sl[j] = x;
+                                bl[j] = ring_lo + x * slot_lo;
+                            }
+                            if (leader_lane) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < m) {
+                                        const uint32_t aj = a_lo + (uint32_t)j * (TC_KB_BYTES >> 4);
+                                        if (!(dflags & 4)) {
+                                            umma2_f16_lo(d_tmem, aj, bl[j], desc_hi, idesc, j == 0 ? acc : 1u);
+                                            umma2_f16_lo(d_tmem, aj + 2, bl[j] + 2, desc_hi, idesc, 1u);
+                                            umma2_f16_lo(d_tmem, aj + 4, bl[j] + 4, desc_hi, idesc, 1u);
+                                            umma2_f16_lo(d_tmem, aj + 6, bl[j] + 6, desc_hi, idesc, 1u);
+                                        }
+                                        umma2_commit_mc(bar_empty + 8 * sl[j], 3);
+                                    }
+                            }
+                            __syncwarp();
+                            acc = 1u;
+                            ready -= (uint32_t)m;
+                            kb += m - 1;                             // (the loop header adds the last one)
+                            if (DBG == 1) step_no += (uint32_t)(m - 1);
+                            slot += (uint32_t)m;
+                            if (slot >= (uint32_t)n_slots) { slot -= (uint32_t)n_slots; ++use; }
+                            continue;
+                        }
+                    }
+#endif
+                    --ready;
                     if (leader_lane && !(dflags & 4)) {
                         if (lo == 0 && hi == 4) {
                             umma2_f16_lo(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
